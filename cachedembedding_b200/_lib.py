@@ -1,0 +1,147 @@
+"""ctypes binding of libcebag_b200.so (C ABI declared in include/cebag.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is missing, or a call is made
+without a CUDA device, this module raises -- it never routes around the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
+
+ABI_VERSION = 1
+
+# cebag_status
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
+EVICT_LFU, EVICT_DATASET = 1, 2
+MODE_SUM, MODE_MEAN = 0, 1
+OPT_SGD, OPT_ROWWISE_ADAGRAD = 0, 1
+LAYOUT_BAG_MAJOR, LAYOUT_SAMPLE_MAJOR = 0, 1
+FREQ_EMPTY = 2**63 - 1
+
+# every symbol include/cebag.h declares (tests check the library exports exactly these)
+EXPORTS = (
+    "cebag_abi_version", "cebag_last_error",
+    "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
+    "cebag_host_device_pointer", "cebag_fill_uniform",
+    "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_flush", "cebag_preload",
+    "cebag_admit_row", "cebag_evict_slot",
+    "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused",
+    "cebag_bag_backward_coo", "cebag_bag_backward_dense", "cebag_bag_backward_weights",
+)
+
+
+class CebagError(RuntimeError):
+    """A libcebag_b200 call failed."""
+
+
+class CacheCapacityError(AssertionError, CebagError):
+    """Unique rows of one prepare_ids call exceed the cache (the reference raises this as an `assert`)."""
+
+
+class Table(Structure):
+    _fields_ = [
+        ("num_rows", c_int64), ("dim", c_int32), ("cache_rows", c_int32), ("strategy", c_int32), ("epoch", c_int32),
+        ("avail", c_int64),
+        ("host_table", c_void_p), ("host_state", c_void_p), ("cache", c_void_p), ("cache_state", c_void_p),
+        ("idx_map", c_void_p), ("row2slot", c_void_p), ("slot2row", c_void_p), ("freq", c_void_p),
+        ("slot_epoch", c_void_p), ("miss_bitmap", c_void_p),
+    ]
+
+
+class Workspace(Structure):
+    _fields_ = [("device", c_void_p), ("device_bytes", c_size_t), ("pinned", c_void_p)]
+
+
+class PrepareStats(Structure):
+    _fields_ = [("unique_hits", c_int64), ("unique_misses", c_int64), ("evicted", c_int64),
+                ("miss_lookups", c_int64), ("total_lookups", c_int64)]
+
+
+class BagArgs(Structure):
+    _fields_ = [
+        ("cache", c_void_p), ("cache_rows", c_int32), ("dim", c_int32),
+        ("slot_ids", c_void_p), ("n", c_int64),
+        ("offsets", c_void_p), ("offsets_are_64", c_int32), ("include_last_offset", c_int32),
+        ("num_bags", c_int64),
+        ("per_sample_weights", c_void_p),
+        ("mode", c_int32),
+        ("padding_idx", c_int64),
+        ("layout", c_int32),
+        ("layout_batch", c_int64),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    lib.cebag_abi_version.restype = c_int
+    lib.cebag_last_error.restype = c_char_p
+    lib.cebag_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
+    lib.cebag_host_free.argtypes = [c_void_p]
+    lib.cebag_host_register.argtypes = [c_void_p, c_size_t]
+    lib.cebag_host_unregister.argtypes = [c_void_p]
+    lib.cebag_host_device_pointer.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.cebag_fill_uniform.argtypes = [c_void_p, c_int64, c_float, c_float, c_uint64, c_void_p]
+    lib.cebag_prepare_workspace_bytes.argtypes = [POINTER(Table), c_int64]
+    lib.cebag_prepare_workspace_bytes.restype = c_size_t
+    lib.cebag_prepare_ids.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),
+                                      POINTER(PrepareStats), c_void_p]
+    lib.cebag_flush.argtypes = [POINTER(Table), POINTER(Workspace), POINTER(c_int64), c_void_p]
+    lib.cebag_preload.argtypes = [POINTER(Table), c_void_p, c_void_p, c_int64, c_void_p]
+    lib.cebag_admit_row.argtypes = [POINTER(Table), c_int64, c_int64, c_void_p]
+    lib.cebag_evict_slot.argtypes = [POINTER(Table), c_int64, c_void_p]
+    lib.cebag_bag_forward.argtypes = [POINTER(BagArgs), c_void_p, c_void_p]
+    lib.cebag_backward_workspace_bytes.argtypes = [POINTER(BagArgs)]
+    lib.cebag_backward_workspace_bytes.restype = c_size_t
+    lib.cebag_bag_backward_fused.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_int32, c_float,
+                                             c_float, c_void_p, c_size_t, c_void_p]
+    lib.cebag_bag_backward_coo.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]
+    lib.cebag_bag_backward_dense.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.cebag_bag_backward_weights.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is c_int and name not in ("cebag_abi_version",):
+            fn.restype = c_int
+
+
+def load():
+    """Return the loaded library; raises if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CebagError(
+            f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+            f"(or `python -c 'import __graft_entry__ as g; g.build()'`).  There is no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    _declare(lib)
+    if lib.cebag_abi_version() != ABI_VERSION:
+        raise CebagError(f"libcebag_b200.so ABI {lib.cebag_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().cebag_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int):
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_CAPACITY:
+        raise CacheCapacityError(msg)
+    if rc == ERR_INDEX:
+        raise IndexError(msg)
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    raise CebagError(msg)
+
+
+__all__ = ["load", "check", "last_error", "Table", "Workspace", "PrepareStats", "BagArgs", "byref", "CebagError",
+           "CacheCapacityError", "EXPORTS", "LIB_PATH"]

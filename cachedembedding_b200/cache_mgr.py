@@ -1,0 +1,348 @@
+"""CachedParamMgr: host-resident table + HBM slot cache + id maps, driven by libcebag_b200's CUDA kernels.
+
+Mirrors ColossalAI's ``colossalai.nn.parallel.layers.cache_embedding.CachedParamMgr`` (the class behind
+``embed.cache_weight_mgr`` at /root/reference/recsys/dlrm_main.py:259; behaviour restated in SURVEY.md Appendix
+A.1/A.3/A.4): same constructor, same methods (``prepare_ids``, ``reorder``, ``flush``, ``print_comm_stats``, the legacy
+single-row helpers), same attributes (``cuda_cached_weight``, ``weight``, ``idx_map``, ``cached_idx_map``,
+``inverted_cached_idx``, ``freq_cnter``, hit/miss histories).  What differs is how the work is done:
+
+* the maps are int32 on the device (``cached_idx_map`` & co. are int64 *views* materialised on access);
+* ``prepare_ids`` is one C call that enqueues hand-written kernels (no sort-based unique/isin/topk) and moves rows
+  between the pinned host table and HBM with zero-copy 128-bit accesses from the GPU (no CPU gather/scatter, no staging
+  buffer, both PCIe directions at once);
+* there is no CPU path: constructing a manager without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import CacheCapacityError  # noqa: F401  (re-export)
+from .evict_strategy import EvictionStrategy
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _PinnedRegistration:
+    """Keeps a host tensor page-locked (in place) for as long as the manager lives."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.ptr = tensor.data_ptr()
+        self.registered = False
+        lib = _lib.load()
+        if not tensor.is_pinned():
+            _lib.check(lib.cebag_host_register(self.ptr, tensor.numel() * tensor.element_size()))
+            self.registered = True
+        dev = ctypes.c_void_p()
+        _lib.check(lib.cebag_host_device_pointer(self.ptr, ctypes.byref(dev)))
+        self.device_ptr = dev.value
+
+    def release(self):
+        if self.registered:
+            try:
+                _lib.load().cebag_host_unregister(self.ptr)
+            except Exception:
+                pass
+            self.registered = False
+
+    def __del__(self):
+        self.release()
+
+
+class CachedParamMgr(nn.Module):
+    """Manage an embedding table whose rows live in host DRAM with a fixed number of them cached in HBM.
+
+    Args mirror upstream (A.1): ``weight`` is the host table fp32[N, D]; ``cuda_row_num`` the number of HBM slots.
+    ``buffer_size`` is accepted for API compatibility: the reference used it to bound the staging buffer of its
+    chunked copier (A.7); rows here move without any staging buffer, so there is nothing to bound.
+    ``with_row_state`` adds one fp32 per row (row-wise Adagrad accumulator) that travels with the row.
+    """
+
+    def __init__(self,
+                 weight: torch.Tensor,
+                 cuda_row_num: int = 0,
+                 buffer_size: int = 0,
+                 pin_weight: bool = True,
+                 evict_strategy: EvictionStrategy = EvictionStrategy.DATASET,
+                 async_copy: bool = False,
+                 with_row_state: bool = False):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise RuntimeError("CachedParamMgr needs a CUDA device: the B200 build has no CPU path")
+        assert weight.dim() == 2 and weight.dtype == torch.float32, "weight must be fp32 [N, D]"
+        assert weight.device.type == "cpu", "the full table lives in host memory"
+        if cuda_row_num == 0:
+            raise NotImplementedError("cuda_row_num == 0")
+        self._lib = _lib.load()
+        self.buffer_size = buffer_size
+        self.num_embeddings, self.embedding_dim = weight.shape
+        assert self.num_embeddings < 2**31, "row ids are int32 on the device"
+        self.cuda_row_num = int(cuda_row_num)
+        self._cuda_available_row_num = self.cuda_row_num
+        self.pin_weight = pin_weight
+        self.elem_size_in_byte = weight.element_size()
+        self._evict_strategy = evict_strategy
+        self._async_copy = async_copy
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+        self.weight = weight.contiguous()
+        # zero-copy row movement needs the table page-locked; register in place (no second copy of the table)
+        self._pin = _PinnedRegistration(self.weight)
+
+        N, C, D = self.num_embeddings, self.cuda_row_num, self.embedding_dim
+        dev = self.device
+        self.cuda_cached_weight = nn.Parameter(torch.zeros(C, D, dtype=torch.float32, device=dev))
+        self.register_buffer("_row2slot", torch.full((N,), -1, dtype=torch.int32, device=dev), persistent=False)
+        self.register_buffer("_slot2row", torch.full((C,), -1, dtype=torch.int32, device=dev), persistent=False)
+        self.register_buffer("_slot_epoch", torch.zeros(C, dtype=torch.int32, device=dev), persistent=False)
+        self.register_buffer("_miss_bitmap", torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev),
+                             persistent=False)
+        self._idx_map: Optional[torch.Tensor] = None     # int32[N]; None == identity
+        if evict_strategy == EvictionStrategy.LFU:
+            self.register_buffer("_freq", torch.full((C,), sys.maxsize, dtype=torch.int64, device=dev),
+                                 persistent=False)
+        else:
+            self._freq = None
+        self.with_row_state = with_row_state
+        if with_row_state:
+            self.row_state = torch.zeros(N, dtype=torch.float32)          # host, travels with the row
+            self._state_pin = _PinnedRegistration(self.row_state)
+            self.register_buffer("cuda_cached_state", torch.zeros(C, dtype=torch.float32, device=dev),
+                                 persistent=False)
+        else:
+            self.row_state = None
+            self._state_pin = None
+            self.cuda_cached_state = None
+        self._epoch = 0
+        self._counters_pinned = torch.zeros(64, dtype=torch.int32).pin_memory()
+
+        self.evict_backlist = torch.tensor([], device=dev)
+        self.num_hits_history: List[int] = []
+        self.num_miss_history: List[int] = []
+        self.num_write_back_history: List[int] = []
+        self._cpu_to_cuda_numel = 0
+        self._cuda_to_cpu_numel = 0
+        self._cache_miss = 0
+        self._total_cache = 0
+        self._elapsed_dict = {"cache_op": 0.0}
+
+    # ---- the C-ABI view of this manager ---------------------------------------------------------------------------
+    def _table(self) -> _lib.Table:
+        t = _lib.Table()
+        t.num_rows = self.num_embeddings
+        t.dim = self.embedding_dim
+        t.cache_rows = self.cuda_row_num
+        t.strategy = _lib.EVICT_LFU if self._evict_strategy == EvictionStrategy.LFU else _lib.EVICT_DATASET
+        t.epoch = self._epoch
+        t.avail = self._cuda_available_row_num
+        t.host_table = self._pin.device_ptr
+        t.host_state = self._state_pin.device_ptr if self._state_pin is not None else None
+        t.cache = self.cuda_cached_weight.data_ptr()
+        t.cache_state = self.cuda_cached_state.data_ptr() if self.cuda_cached_state is not None else None
+        t.idx_map = self._idx_map.data_ptr() if self._idx_map is not None else None
+        t.row2slot = self._row2slot.data_ptr()
+        t.slot2row = self._slot2row.data_ptr()
+        t.freq = self._freq.data_ptr() if self._freq is not None else None
+        t.slot_epoch = self._slot_epoch.data_ptr()
+        t.miss_bitmap = self._miss_bitmap.data_ptr()
+        return t
+
+    def _sync_from(self, t: _lib.Table):
+        self._epoch = t.epoch
+        self._cuda_available_row_num = int(t.avail)
+
+    def _workspace(self, t: _lib.Table, n_ids: int):
+        nbytes = int(self._lib.cebag_prepare_workspace_bytes(ctypes.byref(t), n_ids))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ws = _lib.Workspace(buf.data_ptr(), nbytes, self._counters_pinned.data_ptr())
+        return ws, buf
+
+    # ---- reference-compatible views of the maps (int64, like upstream's buffers) ------------------------------------
+    @property
+    def idx_map(self) -> torch.Tensor:
+        if self._idx_map is None:
+            return torch.arange(self.num_embeddings, dtype=torch.long, device=self.device)
+        return self._idx_map.long()
+
+    @property
+    def cached_idx_map(self) -> torch.Tensor:
+        return self._slot2row.long()
+
+    @property
+    def inverted_cached_idx(self) -> torch.Tensor:
+        return self._row2slot.long()
+
+    @property
+    def freq_cnter(self) -> torch.Tensor:
+        if self._freq is None:
+            raise AttributeError("freq_cnter exists only under EvictionStrategy.LFU")
+        return self._freq
+
+    @property
+    def cuda_available_row_num(self) -> int:
+        return self._cuda_available_row_num
+
+    def cpu_weight_data(self, row_idx: int) -> torch.Tensor:
+        return self.weight.data.view(-1).narrow(0, int(row_idx) * self.embedding_dim,
+                                                self.embedding_dim).view(1, self.embedding_dim)
+
+    @property
+    def cuda_weight(self):
+        return self.cuda_cached_weight
+
+    # ---- A.1 reorder ----------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def reorder(self, ids_freq_mapping=None, warmup_ratio: float = 0.7):
+        """Build the id -> row remap (DATASET) and preload the warm-up rows into slots 0..k-1."""
+        dev = self.device
+        freq = None
+        if ids_freq_mapping is not None:
+            freq = torch.as_tensor(ids_freq_mapping).to(device=dev, dtype=torch.long)
+            assert freq.numel() == self.num_embeddings, "ids_freq_mapping needs one count per id"
+        if freq is not None and self._evict_strategy == EvictionStrategy.DATASET:
+            # id -> rank by descending frequency (stable, so equal counts have one answer)
+            order = torch.argsort(freq, descending=True, stable=True)
+            idx_map = torch.empty(self.num_embeddings, dtype=torch.int32, device=dev)
+            idx_map[order] = torch.arange(self.num_embeddings, dtype=torch.int32, device=dev)
+            self._idx_map = idx_map
+        preload = min(int(np.ceil(self.cuda_row_num * warmup_ratio)), self.num_embeddings)
+        if preload > 0:
+            freq_init = None
+            if self._evict_strategy == EvictionStrategy.LFU and freq is not None:
+                order = torch.argsort(freq, descending=True, stable=True)[:preload]
+                rows = order.to(torch.int32).contiguous()
+                freq_init = freq[order].contiguous()
+            else:
+                rows = torch.arange(preload, dtype=torch.int32, device=dev)
+            t = self._table()
+            _lib.check(self._lib.cebag_preload(ctypes.byref(t), rows.data_ptr(),
+                                               freq_init.data_ptr() if freq_init is not None else None,
+                                               preload, _stream_ptr()))
+            self._sync_from(t)
+            torch.cuda.current_stream().synchronize()   # rows / freq_init are locals
+
+    # ---- A.1 flush ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def flush(self):
+        """Write every resident row back to the host table and empty the cache."""
+        t = self._table()
+        ws, buf = self._workspace(t, 1)
+        written = ctypes.c_int64(0)
+        _lib.check(self._lib.cebag_flush(ctypes.byref(t), ctypes.byref(ws), ctypes.byref(written), _stream_ptr()))
+        self._sync_from(t)
+        self._cuda_to_cpu_numel += written.value * self.embedding_dim
+        assert self._cuda_available_row_num == self.cuda_row_num
+        return written.value
+
+    # ---- A.3 prepare_ids --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def prepare_ids(self, ids: torch.Tensor) -> torch.Tensor:
+        """Make every row that ``ids`` touches resident and return the slot of each id (int64, same order).
+
+        One call covers a whole look-ahead window (reference: recsys/dlrm_main.py:259 passes the concatenation of
+        ``prefetch_num`` batches).  Raises ``CacheCapacityError`` (an ``AssertionError``) with the reference's message
+        when the window's unique rows exceed ``cuda_row_num``; the cache is left unchanged in that case.
+        """
+        start = time.perf_counter()
+        ids = ids.to(device=self.device, dtype=torch.long).contiguous().view(-1)
+        n = ids.numel()
+        out = torch.empty_like(ids)
+        t = self._table()
+        ws, buf = self._workspace(t, n)
+        stats = _lib.PrepareStats()
+        rc = self._lib.cebag_prepare_ids(ctypes.byref(t), ids.data_ptr(), n, out.data_ptr(), ctypes.byref(ws),
+                                         ctypes.byref(stats), _stream_ptr())
+        self._sync_from(t)
+        _lib.check(rc)
+        self._cache_miss += stats.miss_lookups
+        self._total_cache += n
+        self.num_hits_history.append(int(stats.unique_hits))
+        self.num_miss_history.append(int(stats.unique_misses))
+        self.num_write_back_history.append(int(stats.evicted))
+        self._cpu_to_cuda_numel += stats.unique_misses * self.embedding_dim
+        self._cuda_to_cpu_numel += stats.evicted * self.embedding_dim
+        self._elapsed_dict["cache_op"] += time.perf_counter() - start
+        return out
+
+    def _id_to_cached_cuda_id(self, ids: torch.Tensor) -> torch.Tensor:
+        ids = ids.to(self.device).view(-1)
+        rows = ids if self._idx_map is None else self._idx_map[ids].long()
+        return self._row2slot[rows].long()
+
+    @torch.no_grad()
+    def _prepare_rows_on_cuda(self, cpu_row_idxs: torch.Tensor) -> None:
+        """Upstream's inner step (A.4), kept for tests: bring the given (already remapped, non-resident) rows in."""
+        rows = cpu_row_idxs.to(self.device).long().view(-1)
+        if rows.numel() == 0:
+            return
+        if self._idx_map is not None:
+            inv = torch.empty_like(self._idx_map)
+            inv[self._idx_map.long()] = torch.arange(self.num_embeddings, dtype=torch.int32, device=self.device)
+            ids = inv[rows].long()
+        else:
+            ids = rows
+        hits, misses, wb = len(self.num_hits_history), len(self.num_miss_history), len(self.num_write_back_history)
+        freq_before = self._freq.clone() if self._freq is not None else None
+        resident_before = self._row2slot[rows] >= 0
+        slots = self.prepare_ids(ids)
+        # this entry point is not a lookup: undo prepare_ids' bookkeeping (histories, LFU counts of the ids)
+        del self.num_hits_history[hits:], self.num_miss_history[misses:], self.num_write_back_history[wb:]
+        if self._freq is not None:
+            freq_before[slots[~resident_before]] = 0      # A.4 step 6: admitted slots start at 0
+            self._freq.copy_(freq_before)
+
+    # ---- legacy single-row helpers (upstream test_cachemgr, B.1) ------------------------------------------------------------
+    def _row_in_cuda(self, row_id: int) -> bool:
+        return bool(self._row2slot[row_id].item() != -1)
+
+    def _find_free_cuda_row(self) -> int:
+        if self._cuda_available_row_num == 0:
+            return -1
+        return int(torch.nonzero(self._slot2row == -1).squeeze(1)[0].item())
+
+    @torch.no_grad()
+    def _evict(self) -> int:
+        masked = self._slot2row.clone()
+        max_row, slot = torch.max(masked, dim=0)
+        if max_row.item() == -1:
+            raise RuntimeError("Can not evict a row")
+        t = self._table()
+        _lib.check(self._lib.cebag_evict_slot(ctypes.byref(t), int(slot.item()), _stream_ptr()))
+        self._sync_from(t)
+        self._cuda_to_cpu_numel += self.embedding_dim
+        return int(slot.item())
+
+    @torch.no_grad()
+    def _admit(self, row_id: int):
+        slot = self._find_free_cuda_row()
+        if slot == -1:
+            slot = self._evict()
+        t = self._table()
+        _lib.check(self._lib.cebag_admit_row(ctypes.byref(t), int(row_id), slot, _stream_ptr()))
+        self._sync_from(t)
+        self._cpu_to_cuda_numel += self.embedding_dim
+
+    # ---- statistics ------------------------------------------------------------------------------------------------------------
+    def print_comm_stats(self):
+        elapsed = max(self._elapsed_dict["cache_op"], 1e-12)
+        mb_out = self._cuda_to_cpu_numel * self.elem_size_in_byte / 1e6
+        mb_in = self._cpu_to_cuda_numel * self.elem_size_in_byte / 1e6
+        print(f"CUDA->CPU BWD {mb_out / elapsed:.1f} MB/s {mb_out / 1e3:.3f} GB moved in {elapsed:.3f} s of cache_op")
+        print(f"CPU->CUDA BWD {mb_in / elapsed:.1f} MB/s {mb_in / 1e3:.3f} GB moved in {elapsed:.3f} s of cache_op")
+        for k, v in self._elapsed_dict.items():
+            print(f"{k}: {v:.4f} s")
+        if self._total_cache:
+            print(f"cache miss ratio {self._cache_miss / self._total_cache:.4f}")
+
+    def extra_repr(self) -> str:
+        return (f"rows={self.num_embeddings}, dim={self.embedding_dim}, slots={self.cuda_row_num}, "
+                f"evict={self._evict_strategy.name}")

@@ -1,0 +1,461 @@
+// Backward of the embedding bag over the slot cache, fused with the optimizer step on the cached rows
+// (SURVEY.md K12 + K13; replaces _embedding_bag_sparse_backward + coalesce + torch.optim.SGD's sparse branch,
+// reference call sites recsys/dlrm_main.py:274-279).
+//
+// Plan (deterministic, no float atomics):
+//   1. bag_of[i]  : lookup position -> bag                                   (4 B/lookup)
+//   2. radix sort : (slot, value) by slot, stable; value = bag (fast path) or lookup position
+//   3. phase 1    : one group of LANES threads per chunk of kChunk sorted positions walks its runs of equal
+//                   slots, summing w_i * grad_out[bag(i)] in index order.  Runs that lie inside the chunk are
+//                   applied to the cached row at once (row read issued together with the grad reads); the
+//                   first/last run of a chunk that continue into a neighbour are parked as partial sums.
+//   4. phase 2    : one group per run that started in a chunk and crossed its end: adds the parked partials of
+//                   the following chunks in order and applies the update.
+// Algorithmic HBM bytes: 4D per lookup (grad row) + 8D per unique slot (row read + write) + sort traffic
+// (~40 B/lookup).  The same machinery writes a dense [C, D] grad (sparse=False) instead of updating.
+#include "bag_common.cuh"
+#include "radix_sort.cuh"
+
+namespace cebag {
+
+namespace {
+
+constexpr int kBwdThreads = 256;
+constexpr int kChunk = 64;       // sorted positions per group
+constexpr int kUnroll = 4;       // positions in flight per group
+
+enum : int { kOptSgd = 0, kOptAdagrad = 1, kOptDense = 2 };
+enum : unsigned char { kFlagOpenLeft = 1, kFlagOpenRight = 2, kFlagWhole = 4 };
+
+__global__ void __launch_bounds__(256) bag_of_kernel(const BagParams p, int32_t* __restrict__ bag_of) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; g < p.num_bags; g += stride) {
+        int64_t lo = load_offset(p, g), hi = load_offset(p, g + 1);
+        for (int64_t i = lo; i < hi; ++i) bag_of[i] = (int32_t)g;
+    }
+}
+
+// per-lookup weight for the slow path: psw[i] (sum) or 1 / (#non-padding entries of the bag) (mean)
+__global__ void __launch_bounds__(256) lookup_weight_kernel(const BagParams p, float* __restrict__ wts) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; g < p.num_bags; g += stride) {
+        int64_t lo = load_offset(p, g), hi = load_offset(p, g + 1);
+        float scale = 1.f;
+        if (p.mode == CEBAG_MODE_MEAN) {
+            int32_t c = 0;
+            for (int64_t i = lo; i < hi; ++i) c += (p.slot_ids[i] != p.padding_idx);
+            scale = c > 0 ? 1.f / (float)c : 0.f;
+        }
+        for (int64_t i = lo; i < hi; ++i) wts[i] = p.psw ? p.psw[i] * scale : scale;
+    }
+}
+
+struct UpdateParams {
+    float* cache;          // fp32[C, D] updated in place (or dense grad target for kOptDense)
+    float* state;          // fp32[C] row-wise Adagrad accumulators
+    float  lr, eps;
+    int32_t dim;
+};
+
+// apply the accumulated grad `acc` of slot `slot`; `w` holds the current row (prefetched) unless OPT == dense
+template <typename VT, int LANES, int CPL, int OPT>
+__device__ __forceinline__ void apply_update(const UpdateParams& up, int chunks, int lane, uint32_t slot,
+                                             const VT (&acc)[CPL], const VT (&w)[CPL]) {
+    VT* row = reinterpret_cast<VT*>(up.cache) + (int64_t)slot * chunks;
+    if (OPT == kOptDense) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            if (col < chunks) Vec<VT>::st(row + col, acc[c]);
+        }
+        return;
+    }
+    float step = up.lr;
+    if (OPT == kOptAdagrad) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            if (col < chunks) ss += Vec<VT>::dot(acc[c], acc[c]);
+        }
+        ss = group_sum<LANES>(ss);
+        float st = up.state[slot] + ss / (float)up.dim;
+        if (lane == 0) up.state[slot] = st;
+        step = up.lr / (sqrtf(st) + up.eps);
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int col = lane + c * LANES;
+        if (col < chunks) Vec<VT>::st(row + col, Vec<VT>::sub_scaled(w[c], step, acc[c]));
+    }
+}
+
+template <typename VT, int LANES, int CPL>
+__device__ __forceinline__ void store_partial(float* scratch, int64_t chunk, int which, int chunks, int lane,
+                                              const VT (&acc)[CPL]) {
+    VT* dst = reinterpret_cast<VT*>(scratch) + (chunk * 2 + which) * chunks;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int col = lane + c * LANES;
+        if (col < chunks) Vec<VT>::st(dst + col, acc[c]);
+    }
+}
+
+// VAL_IS_BAG: sorted values are bag ids and every weight is 1 (mode sum, no per-sample weights)
+template <typename VT, int LANES, int CPL, int OPT, bool VAL_IS_BAG>
+__global__ void __launch_bounds__(kBwdThreads)
+bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
+                           const uint32_t* __restrict__ vals, const int32_t* __restrict__ bag_of,
+                           const float* __restrict__ wts, const float* __restrict__ grad_out,
+                           float* __restrict__ scratch, unsigned char* __restrict__ flags, int64_t num_chunks) {
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int chunks = p.chunks;
+    const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
+    const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
+
+    for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
+        const int64_t start = ck * kChunk;
+        const int64_t end = min(start + (int64_t)kChunk, p.n);
+        bool first_run = true;
+        const bool open_left = start > 0 && keys[start - 1] == keys[start];
+        unsigned char flag = 0;
+        VT acc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
+        bool pending = false;
+
+        for (int64_t j0 = start; j0 < end; j0 += kUnroll) {
+            uint32_t k[kUnroll];
+            bool live[kUnroll], tail[kUnroll];
+            float w[kUnroll];
+            int64_t grow[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                int64_t j = j0 + u;
+                live[u] = j < end;
+                k[u] = live[u] ? keys[j] : 0u;
+                uint32_t knext = (live[u] && j + 1 < p.n) ? keys[j + 1] : ~k[u];
+                tail[u] = live[u] && knext != k[u];
+                uint32_t v = live[u] ? vals[j] : 0u;
+                int64_t bag = VAL_IS_BAG ? (int64_t)v : (live[u] ? (int64_t)bag_of[v] : 0);
+                w[u] = (VAL_IS_BAG || !live[u]) ? 1.f : wts[v];
+                grow[u] = bag_row(p, bag);
+            }
+            VT g[kUnroll][CPL], wr[kUnroll][CPL];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    int col = lane + c * LANES;
+                    bool ok = live[u] && col < chunks;
+                    g[u][c] = ok ? Vec<VT>::ld_stream(gradv + grow[u] * chunks + col) : Vec<VT>::zero();
+                    // current row, needed where a run ends inside this chunk
+                    bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
+                    wr[u][c] = need_row ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)k[u] * chunks + col)
+                                        : Vec<VT>::zero();
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (!live[u]) continue;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], w[u], g[u][c]);
+                pending = true;
+                if (tail[u]) {
+                    if (first_run && open_left) {
+                        store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
+                        flag |= kFlagOpenLeft;
+                    } else if (k[u] != pad) {
+                        apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, k[u], acc, wr[u]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
+                    first_run = false;
+                    pending = false;
+                }
+            }
+        }
+        if (pending) {  // the last run continues into the next chunk
+            if (first_run && open_left) {
+                store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
+                flag |= kFlagOpenLeft | kFlagWhole;
+            } else {
+                store_partial<VT, LANES, CPL>(scratch, ck, 1, chunks, lane, acc);
+                flag |= kFlagOpenRight;
+            }
+        }
+        if (lane == 0) flags[ck] = flag;
+    }
+}
+
+template <typename VT, int LANES, int CPL, int OPT>
+__global__ void __launch_bounds__(kBwdThreads)
+bag_backward_phase2_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
+                           const float* __restrict__ scratch, const unsigned char* __restrict__ flags,
+                           int64_t num_chunks) {
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int chunks = p.chunks;
+    const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch);
+    const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
+    for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
+        if (!(flags[ck] & kFlagOpenRight)) continue;   // only the chunk that holds the head of a crossing run
+        const uint32_t slot = keys[min(ck * kChunk + (int64_t)kChunk, p.n) - 1];
+        VT acc[CPL], wr[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            acc[c] = col < chunks ? Vec<VT>::ld(sv + (ck * 2 + 1) * chunks + col) : Vec<VT>::zero();
+            wr[c] = (col < chunks && OPT != kOptDense && slot != pad)
+                        ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
+                        : Vec<VT>::zero();
+        }
+        for (int64_t c2 = ck + 1; c2 < num_chunks; ++c2) {
+            unsigned char f = flags[c2];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                int col = lane + c * LANES;
+                if (col < chunks) {
+                    VT part = Vec<VT>::ld(sv + (c2 * 2) * chunks + col);
+                    Vec<VT>::fma(acc[c], 1.f, part);
+                }
+            }
+            if (!(f & kFlagWhole)) break;
+        }
+        if (slot != pad) apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
+    }
+}
+
+// ---- compatibility forms ------------------------------------------------------------------------------------------
+// COO values: values[i] = w_i * grad_out[bag(i)]
+template <typename VT, int LANES, int CPL>
+__global__ void __launch_bounds__(kBwdThreads)
+bag_backward_coo_kernel(const BagParams p, const float* __restrict__ grad_out, float* __restrict__ values) {
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int chunks = p.chunks;
+    const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
+    VT* __restrict__ valv = reinterpret_cast<VT*>(values);
+    for (int64_t g = group; g < p.num_bags; g += num_groups) {
+        int64_t lo = load_offset(p, g), hi = load_offset(p, g + 1);
+        if (hi <= lo) continue;
+        float scale = 1.f;
+        if (p.mode == CEBAG_MODE_MEAN) {
+            int32_t cnt = 0;
+            for (int64_t i = lo; i < hi; ++i) cnt += (p.slot_ids[i] != p.padding_idx);
+            scale = cnt > 0 ? 1.f / (float)cnt : 0.f;
+        }
+        int64_t row = bag_row(p, g);
+        VT gv[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            gv[c] = col < chunks ? Vec<VT>::ld_stream(gradv + row * chunks + col) : Vec<VT>::zero();
+        }
+        for (int64_t i = lo; i < hi; ++i) {
+            float w = (p.psw ? p.psw[i] : 1.f) * scale;
+            if (p.slot_ids[i] == p.padding_idx) w = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                int col = lane + c * LANES;
+                if (col < chunks) Vec<VT>::st_stream(valv + i * chunks + col, Vec<VT>::scale(gv[c], w));
+            }
+        }
+    }
+}
+
+// grad of per_sample_weights: gw[i] = <grad_out[bag(i)], cache[slot_i]>
+template <typename VT, int LANES, int CPL>
+__global__ void __launch_bounds__(kBwdThreads)
+bag_backward_weights_kernel(const BagParams p, const float* __restrict__ grad_out, float* __restrict__ gw) {
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int chunks = p.chunks;
+    const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
+    const VT* __restrict__ cache = reinterpret_cast<const VT*>(p.cache);
+    for (int64_t g = group; g < p.num_bags; g += num_groups) {
+        int64_t lo = load_offset(p, g), hi = load_offset(p, g + 1);
+        if (hi <= lo) continue;
+        int64_t row = bag_row(p, g);
+        VT gv[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            gv[c] = col < chunks ? Vec<VT>::ld_stream(gradv + row * chunks + col) : Vec<VT>::zero();
+        }
+        for (int64_t i = lo; i < hi; ++i) {
+            int64_t s = p.slot_ids[i];
+            float d = 0.f;
+            if (s != p.padding_idx) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    int col = lane + c * LANES;
+                    if (col < chunks) d += Vec<VT>::dot(gv[c], Vec<VT>::ld_stream(cache + s * chunks + col));
+                }
+            }
+            d = group_sum<LANES>(d);
+            if (lane == 0) gw[i] = d;
+        }
+    }
+}
+
+struct BwdLayout {
+    size_t sort, bag_of, wts, scratch, flags, total;
+    int64_t num_chunks;
+};
+
+BwdLayout bwd_layout(int64_t n, int dim) {
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    BwdLayout L;
+    int64_t nn = n > 0 ? n : 1;
+    L.num_chunks = ceil_div(nn, kChunk);
+    size_t off = 0;
+    L.sort = off; off += align(radix_sort_workspace_bytes(nn));
+    L.bag_of = off; off += align((size_t)nn * 4);
+    L.wts = off; off += align((size_t)nn * 4);
+    L.scratch = off; off += align((size_t)L.num_chunks * 2 * dim * 4);
+    L.flags = off; off += align((size_t)L.num_chunks);
+    L.total = off;
+    return L;
+}
+
+int key_bits_for(int32_t cache_rows) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < (int64_t)cache_rows) ++bits;
+    return bits;
+}
+
+template <int OPT>
+int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* target, float* state, float lr,
+                        float eps, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (a->n == 0) return CEBAG_OK;
+    CEBAG_REQUIRE(grad_out != nullptr && target != nullptr, "grad_out / target");
+    CEBAG_REQUIRE(workspace != nullptr, "workspace");
+    CEBAG_REQUIRE(a->n < ((int64_t)1 << 31) && a->num_bags < ((int64_t)1 << 31), "backward size");
+    BwdLayout L = bwd_layout(a->n, a->dim);
+    CEBAG_REQUIRE(workspace_bytes >= L.total, "backward workspace too small");
+    CEBAG_REQUIRE(aligned16(workspace), "workspace alignment");
+    RowShape rs = row_shape(a->dim, aligned16(target) && aligned16(grad_out));
+    BagParams p;
+    int rc = fill_bag_params(a, &p, rs);
+    if (rc) return rc;
+    char* ws = reinterpret_cast<char*>(workspace);
+    int32_t* bag_of = reinterpret_cast<int32_t*>(ws + L.bag_of);
+    float* wts = reinterpret_cast<float*>(ws + L.wts);
+    float* scratch = reinterpret_cast<float*>(ws + L.scratch);
+    unsigned char* flags = reinterpret_cast<unsigned char*>(ws + L.flags);
+    const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
+
+    bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
+    CEBAG_LAUNCH_CHECK();
+    if (!fast) {
+        lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);
+        CEBAG_LAUNCH_CHECK();
+    }
+    const uint32_t *keys = nullptr, *vals = nullptr;
+    rc = radix_sort_slots(a->slot_ids, a->n, key_bits_for(a->cache_rows), ws + L.sort,
+                          radix_sort_workspace_bytes(a->n), fast ? reinterpret_cast<const uint32_t*>(bag_of) : nullptr,
+                          &keys, &vals, stream);
+    if (rc) return rc;
+    UpdateParams up;
+    up.cache = target;
+    up.state = state;
+    up.lr = lr;
+    up.eps = eps;
+    up.dim = a->dim;
+#define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
+    do {                                                                                                            \
+        int grid = grid_for(L.num_chunks * LANES, kBwdThreads, 4);                                                  \
+        if (fast)                                                                                                   \
+            bag_backward_phase1_kernel<VT, LANES, CPL, OPT, true><<<grid, kBwdThreads, 0, stream>>>(                \
+                p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                            \
+        else                                                                                                        \
+            bag_backward_phase1_kernel<VT, LANES, CPL, OPT, false><<<grid, kBwdThreads, 0, stream>>>(               \
+                p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                            \
+        bag_backward_phase2_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(p, up, keys, scratch,     \
+                                                                                          flags, L.num_chunks);     \
+    } while (0)
+    CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);
+#undef LAUNCH_BWD
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
+}
+
+}  // namespace
+}  // namespace cebag
+
+using namespace cebag;
+
+extern "C" size_t cebag_backward_workspace_bytes(const cebag_bag_args* a) {
+    if (!a) return 0;
+    return bwd_layout(a->n, a->dim).total;
+}
+
+extern "C" int cebag_bag_backward_fused(const cebag_bag_args* a, const float* grad_out, float* cache_rw,
+                                        float* cache_state, int32_t optimizer, float lr, float eps, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(a != nullptr, "null args");
+    if (optimizer == CEBAG_OPT_SGD)
+        return run_sorted_backward<kOptSgd>(a, grad_out, cache_rw, nullptr, lr, 0.f, workspace, workspace_bytes, stream);
+    if (optimizer == CEBAG_OPT_ROWWISE_ADAGRAD) {
+        CEBAG_REQUIRE(cache_state != nullptr, "row-wise Adagrad needs cache_state");
+        return run_sorted_backward<kOptAdagrad>(a, grad_out, cache_rw, cache_state, lr, eps, workspace,
+                                                workspace_bytes, stream);
+    }
+    set_error("unknown optimizer %d", optimizer);
+    return CEBAG_ERR_INVALID;
+}
+
+extern "C" int cebag_bag_backward_dense(const cebag_bag_args* a, const float* grad_out, float* grad_cache,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(a != nullptr && grad_cache != nullptr, "null args");
+    CEBAG_CUDA_CHECK(cudaMemsetAsync(grad_cache, 0, (size_t)a->cache_rows * a->dim * sizeof(float), stream));
+    return run_sorted_backward<kOptDense>(a, grad_out, grad_cache, nullptr, 0.f, 0.f, workspace, workspace_bytes,
+                                          stream);
+}
+
+extern "C" int cebag_bag_backward_coo(const cebag_bag_args* a, const float* grad_out, float* values, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(a != nullptr, "null args");
+    if (a->n == 0 || a->num_bags == 0) return CEBAG_OK;
+    CEBAG_REQUIRE(grad_out != nullptr && values != nullptr, "grad_out / values");
+    RowShape rs = row_shape(a->dim, aligned16(values) && aligned16(grad_out));
+    BagParams p;
+    int rc = fill_bag_params(a, &p, rs);
+    if (rc) return rc;
+#define LAUNCH_COO(VT, LANES, CPL)                                                                 \
+    bag_backward_coo_kernel<VT, LANES, CPL><<<grid_for(p.num_bags * LANES, kBwdThreads, 8), kBwdThreads, 0, stream>>>( \
+        p, grad_out, values)
+    CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_COO);
+#undef LAUNCH_COO
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_bag_backward_weights(const cebag_bag_args* a, const float* grad_out, float* grad_weights,
+                                          void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(a != nullptr, "null args");
+    if (a->n == 0 || a->num_bags == 0) return CEBAG_OK;
+    CEBAG_REQUIRE(grad_out != nullptr && grad_weights != nullptr, "grad_out / grad_weights");
+    RowShape rs = row_shape(a->dim, aligned16(a->cache) && aligned16(grad_out));
+    BagParams p;
+    int rc = fill_bag_params(a, &p, rs);
+    if (rc) return rc;
+#define LAUNCH_GW(VT, LANES, CPL)                                                                  \
+    bag_backward_weights_kernel<VT, LANES, CPL><<<grid_for(p.num_bags * LANES, kBwdThreads, 8), kBwdThreads, 0, stream>>>( \
+        p, grad_out, grad_weights)
+    CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_GW);
+#undef LAUNCH_GW
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
+}

@@ -1,0 +1,78 @@
+// Shared helpers for the sm_100a kernels of libcebag_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cebag.h"
+
+namespace cebag {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void set_error(const char* fmt, ...);
+
+#define CEBAG_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cebag::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CEBAG_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+#define CEBAG_LAUNCH_CHECK()  CEBAG_CUDA_CHECK(cudaGetLastError())
+
+#define CEBAG_REQUIRE(cond, msg)                                                                   \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            cebag::set_error("invalid argument: %s (%s)", msg, #cond);                             \
+            return CEBAG_ERR_INVALID;                                                              \
+        }                                                                                          \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid for a grid-stride kernel: enough CTAs for the work, capped at `waves` resident waves of the 148 SMs
+static inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
+    int64_t need = ceil_div(work_items, threads);
+    int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ---- 128-bit global memory access -------------------------------------------------------------------------------
+// streaming load: read-only path, do not allocate in L1 (rows are touched once per kernel)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// plain (coherent) 128-bit load for data that this kernel also writes
+__device__ __forceinline__ float4 ld_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_f4(float4* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
+__device__ __forceinline__ void add4(float4& acc, const float4& v) {
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace cebag

@@ -1,0 +1,93 @@
+// Pinned host memory for the table, error reporting, and the counter-based uniform fill.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace cebag {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+// splitmix64 finaliser: element i of stream `seed` depends only on (seed, i)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ float uniform_at(uint64_t seed, int64_t i, float lo, float span) {
+    uint32_t bits = (uint32_t)(mix64(seed ^ mix64((uint64_t)i)) >> 40);   // 24 random bits
+    return lo + span * ((float)bits * (1.0f / 16777216.0f));
+}
+
+__global__ void __launch_bounds__(256)
+fill_uniform_kernel(float* __restrict__ dst, int64_t count, float lo, float span, uint64_t seed, int vec) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (vec) {
+        int64_t n4 = count / 4;
+        for (int64_t q = tid; q < n4; q += stride) {
+            float4 v = make_float4(uniform_at(seed, 4 * q, lo, span), uniform_at(seed, 4 * q + 1, lo, span),
+                                   uniform_at(seed, 4 * q + 2, lo, span), uniform_at(seed, 4 * q + 3, lo, span));
+            reinterpret_cast<float4*>(dst)[q] = v;
+        }
+        for (int64_t i = n4 * 4 + tid; i < count; i += stride) dst[i] = uniform_at(seed, i, lo, span);
+    } else {
+        for (int64_t i = tid; i < count; i += stride) dst[i] = uniform_at(seed, i, lo, span);
+    }
+}
+
+}  // namespace
+}  // namespace cebag
+
+using namespace cebag;
+
+extern "C" int cebag_abi_version(void) { return CEBAG_ABI_VERSION; }
+
+extern "C" const char* cebag_last_error(void) { return g_error; }
+
+extern "C" int cebag_host_alloc(void** out_ptr, size_t bytes) {
+    CEBAG_REQUIRE(out_ptr != nullptr && bytes > 0, "host_alloc arguments");
+    CEBAG_CUDA_CHECK(cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_host_free(void* ptr) {
+    if (ptr) CEBAG_CUDA_CHECK(cudaFreeHost(ptr));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_host_register(void* ptr, size_t bytes) {
+    CEBAG_REQUIRE(ptr != nullptr && bytes > 0, "host_register arguments");
+    CEBAG_CUDA_CHECK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_host_unregister(void* ptr) {
+    if (ptr) CEBAG_CUDA_CHECK(cudaHostUnregister(ptr));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_host_device_pointer(void* host_ptr, void** out_dev_ptr) {
+    CEBAG_REQUIRE(host_ptr != nullptr && out_dev_ptr != nullptr, "host_device_pointer arguments");
+    CEBAG_CUDA_CHECK(cudaHostGetDevicePointer(out_dev_ptr, host_ptr, 0));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi, uint64_t seed, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(dst != nullptr && count >= 0, "fill_uniform arguments");
+    if (count == 0) return CEBAG_OK;
+    fill_uniform_kernel<<<kNumSMs * 8, 256, 0, stream>>>(dst, count, lo, hi - lo, seed, aligned16(dst) ? 1 : 0);
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
+}

@@ -1,0 +1,133 @@
+"""ParallelCachedEmbeddingBagTablewise: table-wise sharded cached embedding bag.
+
+Drop-in for ``colossalai.nn.parallel.layers.ParallelCachedEmbeddingBagTablewise`` as constructed at
+/root/reference/recsys/models/dlrm.py:53-68: every rank owns whole tables (concatenated into one local table with
+re-based ids), looks up the GLOBAL batch for its tables, and one all-to-all of pooled embeddings gives every rank its
+slice of the batch with all features (rank-major feature order).
+
+The bag kernel writes the local result directly in (B, F_loc, D) order, so upstream's
+``torch.cat(out.split(B), 1)`` repack before the all-to-all disappears (forward and backward).
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .cached_embedding import CachedEmbeddingBag
+from .collectives import dual_all_to_all_tablewise, split_sizes
+from .embedding_config import TablewiseEmbeddingBagConfig
+from .evict_strategy import EvictionStrategy
+from .parallel_cached_embedding import _world
+
+
+class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
+    """All tables assigned to this rank are handled by ONE cached bag (one host table, one slot cache)."""
+
+    def __init__(self,
+                 embedding_bag_config_list: List[TablewiseEmbeddingBagConfig],
+                 embedding_dim: int,
+                 padding_idx=None,
+                 max_norm=None,
+                 norm_type=2.,
+                 scale_grad_by_freq=False,
+                 sparse=False,
+                 _weight=None,
+                 mode='mean',
+                 include_last_offset=False,
+                 dtype=None,
+                 device=None,
+                 cache_ratio=0.01,
+                 warmup_ratio=0.7,
+                 buffer_size=50_000,
+                 pin_weight=False,
+                 evict_strategy: EvictionStrategy = EvictionStrategy.LFU,
+                 process_group=None,
+                 **kwargs):
+        self.process_group = process_group
+        self.rank, self.world_size = _world(process_group)
+        self.rank_of_tables = [config.assigned_rank for config in embedding_bag_config_list]
+        self.global_table_num_embeddings_list = [config.num_embeddings for config in embedding_bag_config_list]
+        self.global_tables_num = len(embedding_bag_config_list)
+        self.global_tables_offsets = torch.cumsum(
+            torch.tensor([0] + self.global_table_num_embeddings_list), 0)
+        self.assigned_table_list: List[int] = [i for i, r in enumerate(self.rank_of_tables) if r == self.rank]
+        assert self.assigned_table_list, f"rank {self.rank} owns no table"
+        num_embeddings = sum(self.global_table_num_embeddings_list[i] for i in self.assigned_table_list)
+
+        # ids_freq_mapping of the local tables, concatenated (None if any table has none)
+        ids_freq_mapping = []
+        for i in self.assigned_table_list:
+            m = embedding_bag_config_list[i].ids_freq_mapping
+            if m is None:
+                ids_freq_mapping = None
+                break
+            ids_freq_mapping.append(torch.as_tensor(m))
+        if ids_freq_mapping is not None:
+            ids_freq_mapping = torch.cat(ids_freq_mapping)
+        if _weight is None:
+            ws = [embedding_bag_config_list[i].initial_weight for i in self.assigned_table_list]
+            if all(w is not None for w in ws):
+                _weight = torch.cat([w.detach().cpu().float() for w in ws], 0).contiguous()
+
+        # global id -> local row: subtract the rows of the NON-local tables that precede each local table
+        self.idx_offset_list = []
+        local_prefix = 0
+        for i in self.assigned_table_list:
+            self.idx_offset_list.append(int(self.global_tables_offsets[i]) - local_prefix)
+            local_prefix += self.global_table_num_embeddings_list[i]
+        self.embedding_dim_per_rank = [0 for _ in range(self.world_size)]
+        for r in self.rank_of_tables:
+            self.embedding_dim_per_rank[r] += embedding_dim
+
+        super().__init__(num_embeddings, embedding_dim, padding_idx, max_norm, norm_type, scale_grad_by_freq, sparse,
+                         _weight, mode, include_last_offset, dtype, device, cache_ratio, ids_freq_mapping,
+                         warmup_ratio, buffer_size, pin_weight, evict_strategy, **kwargs)
+        self.cache_op = True
+
+    def forward(self, indices: torch.Tensor, offsets: torch.Tensor = None, per_sample_weights=None, shape_hook=None,
+                already_split_along_rank=True):
+        n_local = len(self.assigned_table_list)
+        if not already_split_along_rank:
+            n_off = offsets.shape[0] - (1 if self.include_last_offset else 0)
+            batch_size = n_off // self.global_tables_num
+            indices, offsets, per_sample_weights = self.split_along_rank(batch_size, indices, offsets,
+                                                                         per_sample_weights)
+        else:
+            batch_size = offsets.shape[0] // n_local
+        if self.cache_op:
+            with torch.no_grad():
+                indices = self.cache_weight_mgr.prepare_ids(indices)
+        # (B, F_loc, D) written by the kernel == torch.cat(out.split(B), 1) of the bag-major result
+        local_out = self._embed(indices, offsets, per_sample_weights, layout="sample_major", layout_batch=batch_size)
+        local_out = local_out.view(batch_size, n_local * self.embedding_dim)
+        scatter_strides = split_sizes(batch_size, self.world_size)
+        output_full = dual_all_to_all_tablewise(local_out, self.process_group, scatter_strides,
+                                                self.embedding_dim_per_rank)
+        if shape_hook is not None:
+            output_full = shape_hook(output_full)
+        return output_full
+
+    def split_along_rank(self, batch_size, indices: torch.Tensor, offsets: torch.Tensor = None,
+                         per_sample_weights=None):
+        """Cut this rank's tables out of a global KJT (values = global ids, feature-major offsets)."""
+        li, lo, lw = [], [], []
+        pre_end = 0
+        # table boundaries on the host once (upstream does .item() per table)
+        bounds = offsets[torch.arange(0, offsets.shape[0], batch_size, device=offsets.device)].tolist()
+        for k, t in enumerate(self.assigned_table_list):
+            start = bounds[t]
+            if (not self.include_last_offset) and batch_size * (t + 1) >= offsets.shape[0]:
+                end = indices.shape[0]
+            else:
+                end = bounds[t + 1]
+            li.append(indices.narrow(0, start, end - start) - self.idx_offset_list[k])
+            if per_sample_weights is not None:
+                lw.append(per_sample_weights.narrow(0, start, end - start))
+            last = (k + 1 == len(self.assigned_table_list))
+            take = batch_size + 1 if (last and self.include_last_offset) else batch_size
+            lo.append(offsets.narrow(0, batch_size * t, take) + (pre_end - start))
+            pre_end += end - start
+        return (torch.cat(li), torch.cat(lo), torch.cat(lw) if per_sample_weights is not None else None)
+
+    def set_cache_op(self, cache_op: bool = True):
+        self.cache_op = cache_op

@@ -1,0 +1,176 @@
+/*
+ * cebag.h -- C ABI of the B200-native cached embedding-bag hot path (libcebag_b200.so).
+ *
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.  Device pointers are raw
+ * CUDA addresses, `stream` is a cudaStream_t passed as void*.  Every entry point returns a cebag_status
+ * (0 = ok) and never throws; cebag_last_error() gives the message of the last failure on the calling thread.
+ *
+ * The reference (hpcaitech/CachedEmbedding) has no FFI for this path: its boundary is the Python nn.Module
+ * surface of ColossalAI's cache_embedding package (pinned in /root/reference/README.md:37, absent from the
+ * tree; behaviour restated in SURVEY.md Appendix A).  Each entry point below cites the reference call site /
+ * upstream method it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ */
+#ifndef CEBAG_H_
+#define CEBAG_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEBAG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CEBAG_API __attribute__((visibility("default")))
+#else
+#define CEBAG_API
+#endif
+
+typedef enum cebag_status {
+    CEBAG_OK = 0,
+    CEBAG_ERR_INVALID = 1,   /* bad argument (null pointer, bad size, unsupported mode)          */
+    CEBAG_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed                       */
+    CEBAG_ERR_CAPACITY = 3,  /* unique rows of one prepare_ids call exceed the cache (A.3 assert) */
+    CEBAG_ERR_INDEX = 4      /* an id outside [0, num_rows) was seen                               */
+} cebag_status;
+
+enum { CEBAG_EVICT_LFU = 1, CEBAG_EVICT_DATASET = 2 };        /* EvictionStrategy (recsys/models/dlrm.py:66,80) */
+enum { CEBAG_MODE_SUM = 0, CEBAG_MODE_MEAN = 1 };              /* F.embedding_bag mode                           */
+enum { CEBAG_OPT_SGD = 0, CEBAG_OPT_ROWWISE_ADAGRAD = 1 };
+enum { CEBAG_LAYOUT_BAG_MAJOR = 0,     /* out[g, :]                       -- what F.embedding_bag returns            */
+       CEBAG_LAYOUT_SAMPLE_MAJOR = 1   /* out[(g % B) * F + g / B, :]     -- the (B, F, D) view the DLRM shape hooks
+                                          build (recsys/models/dlrm.py:26-30), written directly by the kernel   */ };
+
+#define CEBAG_FREQ_EMPTY INT64_MAX     /* LFU counter of an empty slot (upstream: sys.maxsize)                   */
+
+/*
+ * State of one cached table.  All arrays are owned by the caller (the Python module allocates them as torch
+ * tensors); the library only reads/writes through these pointers.  Mirrors CachedParamMgr's buffers (A.1):
+ *   weight -> host_table, cuda_cached_weight -> cache, idx_map, cached_idx_map -> slot2row,
+ *   inverted_cached_idx -> row2slot, freq_cnter -> freq.
+ * B200-first differences: the id maps are int32 (half the HBM of the reference's int64 maps, which were 76 % of
+ * its footprint); idx_map may be NULL (identity) ; a per-slot window stamp and a per-row miss
+ * bitmap replace the reference's sort-based unique/isin.
+ */
+typedef struct cebag_table {
+    int64_t   num_rows;       /* N: rows of the host table                                                */
+    int32_t   dim;            /* D: floats per row                                                        */
+    int32_t   cache_rows;     /* C: slots in HBM                                                          */
+    int32_t   strategy;       /* CEBAG_EVICT_*                                                            */
+    int32_t   epoch;          /* window stamp, advanced by every prepare_ids (library-maintained)         */
+    int64_t   avail;          /* free slots (library-maintained; upstream _cuda_available_row_num)        */
+    float*    host_table;     /* fp32[N, D]  pinned host memory, device-visible address                   */
+    float*    host_state;     /* fp32[N]     row-wise Adagrad state in pinned host memory, or NULL        */
+    float*    cache;          /* fp32[C, D]  HBM                                                          */
+    float*    cache_state;    /* fp32[C]     HBM, or NULL                                                 */
+    const int32_t* idx_map;   /* int32[N] id -> row, or NULL for identity                                 */
+    int32_t*  row2slot;       /* int32[N]   -1 = not resident                                             */
+    int32_t*  slot2row;       /* int32[C]   -1 = empty                                                    */
+    int64_t*  freq;           /* int64[C]   LFU counters (CEBAG_FREQ_EMPTY = empty); NULL for DATASET     */
+    int32_t*  slot_epoch;     /* int32[C]   stamp of the last prepare_ids window that used the slot       */
+    uint32_t* miss_bitmap;    /* uint32[ceil(N/32)] all-zero between calls                                */
+} cebag_table;
+
+/* Scratch for one prepare_ids / flush call; sizes from cebag_prepare_workspace_bytes(). */
+typedef struct cebag_workspace {
+    void*  device;            /* device scratch                                                           */
+    size_t device_bytes;
+    void*  pinned;            /* >= 256 bytes of pinned host memory for counter read-back                 */
+} cebag_workspace;
+
+/* What one prepare_ids call did (upstream: num_hits_history / num_miss_history / num_write_back_history,
+ * _cache_miss, _total_cache, _cpu_to_cuda_numel, _cuda_to_cpu_numel). */
+typedef struct cebag_prepare_stats {
+    int64_t unique_hits;      /* unique rows of the call already resident                                 */
+    int64_t unique_misses;    /* unique rows brought in (M)                                               */
+    int64_t evicted;          /* rows written back to the host table (E)                                  */
+    int64_t miss_lookups;     /* ids (with multiplicity) whose row was not resident                       */
+    int64_t total_lookups;    /* n                                                                        */
+} cebag_prepare_stats;
+
+CEBAG_API int         cebag_abi_version(void);
+CEBAG_API const char* cebag_last_error(void);
+
+/* ---- pinned host memory for the table (upstream: weight.pin_memory(), A.1) --------------------------------- */
+CEBAG_API int cebag_host_alloc(void** out_ptr, size_t bytes);                 /* cudaHostAlloc(portable|mapped)          */
+CEBAG_API int cebag_host_free(void* ptr);
+CEBAG_API int cebag_host_register(void* ptr, size_t bytes);                   /* pin an existing allocation in place     */
+CEBAG_API int cebag_host_unregister(void* ptr);
+CEBAG_API int cebag_host_device_pointer(void* host_ptr, void** out_dev_ptr);  /* device-visible alias of a pinned ptr    */
+
+/* Fill fp32[count] (device or pinned host memory) with U(lo, hi) from a counter-based generator; the value of
+ * element i depends only on (seed, i).  Replaces _weight_alloc's uniform_(-1/N, 1/N) (A.2) for tables that are
+ * too large to initialise from one host thread. */
+CEBAG_API int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi, uint64_t seed, void* stream);
+
+/* ---- cache manager (CachedParamMgr) ---------------------------------------------------------------------------- */
+CEBAG_API size_t cebag_prepare_workspace_bytes(const cebag_table* t, int64_t n_ids);
+
+/* CachedParamMgr.prepare_ids(ids) (A.3 + A.4; called at recsys/dlrm_main.py:259 and inside forward when cache_op).
+ * ids: int64[n] on the device.  slot_ids_out: int64[n] on the device, slot of every id, same order.
+ * Performs unique / miss detection / victim selection / write-back of victims to the host table / fill of missed
+ * rows / map + LFU counter update.  Synchronises `stream` once (counter read-back) before any state is changed,
+ * so a CEBAG_ERR_CAPACITY / CEBAG_ERR_INDEX return leaves the table untouched; `stats` is filled either way. */
+CEBAG_API int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
+                      const cebag_workspace* ws, cebag_prepare_stats* stats, void* stream);
+
+/* CachedParamMgr.flush() (A.1): write every resident row (and state) back to the host table, empty the maps.
+ * Returns the number of rows written in *rows_written.  Synchronises `stream`. */
+CEBAG_API int cebag_flush(cebag_table* t, const cebag_workspace* ws, int64_t* rows_written, void* stream);
+
+/* Warm-up preload of CachedParamMgr.reorder() (A.1 step 2): rows[k] (int32, device) go to slots 0..k-1;
+ * freq_init (int64[k], device) seeds the LFU counters, NULL means 0.  The cache must be empty. */
+CEBAG_API int cebag_preload(cebag_table* t, const int32_t* rows, const int64_t* freq_init, int64_t k, void* stream);
+
+/* Single-row legacy helpers of upstream test_cachemgr (B.1): _admit(row) into `slot`, _evict of `slot`. */
+CEBAG_API int cebag_admit_row(cebag_table* t, int64_t row, int64_t slot, void* stream);
+CEBAG_API int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream);
+
+/* ---- embedding bag over the slot cache (F.embedding_bag on cuda_cached_weight, A.2) --------------------------- */
+typedef struct cebag_bag_args {
+    const float*   cache;          /* fp32[C, D]                                                            */
+    int32_t        cache_rows;     /* C                                                                     */
+    int32_t        dim;            /* D                                                                     */
+    const int64_t* slot_ids;       /* int64[n]                                                              */
+    int64_t        n;              /* lookups                                                               */
+    const void*    offsets;        /* int32 or int64 [num_bags] or [num_bags + 1]                           */
+    int32_t        offsets_are_64; /* 1: int64 offsets, 0: int32                                            */
+    int32_t        include_last_offset;
+    int64_t        num_bags;       /* G                                                                     */
+    const float*   per_sample_weights; /* fp32[n] or NULL                                                   */
+    int32_t        mode;           /* CEBAG_MODE_*                                                          */
+    int64_t        padding_idx;    /* slot id to skip, or -1                                                */
+    int32_t        layout;         /* CEBAG_LAYOUT_* of out / grad_out                                      */
+    int64_t        layout_batch;   /* B for CEBAG_LAYOUT_SAMPLE_MAJOR (num_bags == F * B)                   */
+} cebag_bag_args;
+
+/* forward: out fp32[G, D] (or sample-major).  Replaces F.embedding_bag (recsys/models/dlrm.py:99-110). */
+CEBAG_API int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stream);
+
+CEBAG_API size_t cebag_backward_workspace_bytes(const cebag_bag_args* a);
+
+/* backward fused with the optimizer step on the cached rows: replaces _embedding_bag_sparse_backward +
+ * coalesce + torch.optim.SGD's sparse branch (recsys/dlrm_main.py:274-279; A.8).  cache is updated in place:
+ *   SGD:             W[s] -= lr * sum_i w_i * grad_out[bag(i)]
+ *   row-wise Adagrad: g = that sum;  state[s] += mean(g^2);  W[s] -= lr * g / (sqrt(state[s]) + eps)
+ * Deterministic: lookups are radix-sorted by slot and reduced in index order; no float atomics. */
+CEBAG_API int cebag_bag_backward_fused(const cebag_bag_args* a, const float* grad_out, float* cache_rw, float* cache_state,
+                             int32_t optimizer, float lr, float eps, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* backward, compatibility forms for an external torch optimizer:
+ *   coo:   values fp32[n, D] with values[i] = w_i * grad_out[bag(i)] (indices are slot_ids) -- the COO grad that
+ *          sparse=True produces;  dense: grad fp32[C, D] fully written (zeros + segment sums) for sparse=False. */
+CEBAG_API int cebag_bag_backward_coo(const cebag_bag_args* a, const float* grad_out, float* values, void* stream);
+CEBAG_API int cebag_bag_backward_dense(const cebag_bag_args* a, const float* grad_out, float* grad_cache, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* grad w.r.t. per_sample_weights (mode sum): gw[i] = <grad_out[bag(i)], cache[slot_i]>. */
+CEBAG_API int cebag_bag_backward_weights(const cebag_bag_args* a, const float* grad_out, float* grad_weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEBAG_H_ */

@@ -1,0 +1,463 @@
+"""Parity of the CUDA path (through the C-ABI library) with the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact cache-slot assignment and id->slot maps; pooled sums and updated rows
+within 1e-5 relative fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import EvictionStrategy as OStrategy
+from oracle import OracleCachedEmbeddingBag, rowwise_adagrad_reference
+
+RTOL, ATOL = 1e-5, 1e-7   # north_star: 1e-5 relative fp32 (atol covers sums that cancel to ~0)
+
+
+def _mods():
+    import cachedembedding_b200 as ce
+    return ce
+
+
+def make_bags(N, D, G, max_len, gen, include_last=True, empty_frac=0.2):
+    lens = torch.randint(0, max_len + 1, (G,), generator=gen)
+    lens[torch.rand(G, generator=gen) < empty_frac] = 0
+    offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(lens, 0)])
+    n = int(offsets[-1])
+    ids = torch.randint(0, N, (n,), generator=gen)
+    if not include_last:
+        offsets = offsets[:-1]
+    return ids, offsets
+
+
+def assert_maps_equal(mgr, omgr):
+    assert torch.equal(mgr.cached_idx_map.cpu(), omgr.cached_idx_map), "slot -> row map differs"
+    assert torch.equal(mgr.inverted_cached_idx.cpu(), omgr.inverted_cached_idx), "row -> slot map differs"
+    assert torch.equal(mgr.idx_map.cpu(), omgr.idx_map), "id -> row map differs"
+    assert mgr.cuda_available_row_num == omgr.cuda_available_row_num
+    if hasattr(omgr, "freq_cnter"):
+        assert torch.equal(mgr.freq_cnter.cpu(), omgr.freq_cnter), "LFU counters differ"
+
+
+# ---------------------------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("D", [128, 16, 32, 64, 256, 512, 5, 36, 8, 1, 100])
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_forward_matches_oracle(D, mode):
+    ce = _mods()
+    gen = torch.Generator().manual_seed(D * 7 + len(mode))
+    C, G = 300, 257
+    weight = torch.randn(C, D, generator=gen)
+    slots, offsets = make_bags(C, D, G, 9, gen)
+    ref = torch.nn.functional.embedding_bag(slots, weight, offsets, mode=mode, include_last_offset=True)
+    out = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.cuda(), include_last_offset=True, mode=mode)
+    torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("offset_dtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("include_last", [True, False])
+def test_forward_offsets_variants_weights_padding(offset_dtype, include_last):
+    ce = _mods()
+    gen = torch.Generator().manual_seed(5)
+    C, D, G = 64, 128, 100
+    weight = torch.randn(C, D, generator=gen)
+    slots, offsets = make_bags(C, D, G, 6, gen, include_last=include_last)
+    psw = torch.randn(slots.numel(), generator=gen)
+    for pad in (None, 3):
+        ref = torch.nn.functional.embedding_bag(slots, weight, offsets, mode="sum", per_sample_weights=psw,
+                                                include_last_offset=include_last, padding_idx=pad)
+        out = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.to(offset_dtype).cuda(), psw.cuda(),
+                                      include_last_offset=include_last, mode="sum", padding_idx=pad)
+        torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+        refm = torch.nn.functional.embedding_bag(slots, weight, offsets, mode="mean",
+                                                 include_last_offset=include_last, padding_idx=pad)
+        outm = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.to(offset_dtype).cuda(),
+                                       include_last_offset=include_last, mode="mean", padding_idx=pad)
+        torch.testing.assert_close(outm.cpu(), refm, rtol=RTOL, atol=ATOL)
+
+
+def test_forward_2d_input_and_empty():
+    ce = _mods()
+    gen = torch.Generator().manual_seed(9)
+    weight = torch.randn(50, 16, generator=gen)
+    idx2d = torch.randint(0, 50, (7, 3), generator=gen)
+    ref = torch.nn.functional.embedding_bag(idx2d, weight, mode="sum")
+    out = ce.embedding_bag_cached(weight.cuda(), idx2d.cuda(), None, mode="sum")
+    torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+    # no lookups at all: G bags, all empty
+    out = ce.embedding_bag_cached(weight.cuda(), torch.empty(0, dtype=torch.long).cuda(),
+                                  torch.zeros(5, dtype=torch.long).cuda(), include_last_offset=True, mode="sum")
+    assert out.shape == (4, 16) and float(out.abs().sum()) == 0.0
+
+
+def test_forward_sample_major_layout():
+    ce = _mods()
+    gen = torch.Generator().manual_seed(10)
+    C, D, F, B = 40, 128, 5, 12
+    weight = torch.randn(C, D, generator=gen)
+    slots, offsets = make_bags(C, D, F * B, 3, gen)
+    ref = torch.nn.functional.embedding_bag(slots, weight, offsets, mode="sum", include_last_offset=True)
+    ref = torch.cat(ref.split(B), 1)    # (B, F*D): what the table-wise bag sends to the all-to-all
+    out = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum",
+                                  layout="sample_major", layout_batch=B)
+    torch.testing.assert_close(out.view(B, F * D).cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
+# ---------------------------------------------------------------------------------------------------- backward
+class _Owner:
+    """Minimal stand-in for the module the autograd function consults for its backward mode."""
+
+    def __init__(self, sparse=True, fused=None, state=None):
+        self.sparse = sparse
+        self._fused_optimizer = fused
+        self.cache_weight_mgr = type("M", (), {"cuda_cached_state": state})()
+
+
+@pytest.mark.parametrize("D", [128, 16, 5, 256, 64])
+@pytest.mark.parametrize("mode,use_psw", [("sum", False), ("sum", True), ("mean", False)])
+def test_backward_sparse_dense_and_fused_sgd(D, mode, use_psw):
+    ce = _mods()
+    from cachedembedding_b200 import _lib
+    gen = torch.Generator().manual_seed(D + 31 * use_psw)
+    C, G = 97, 400          # few slots, many lookups: long runs of duplicates that cross chunk boundaries
+    weight = torch.randn(C, D, generator=gen)
+    slots, offsets = make_bags(C, D, G, 7, gen)
+    slots[: slots.numel() // 3] = 11      # one very hot slot
+    psw = torch.randn(slots.numel(), generator=gen) if use_psw else None
+    grad = torch.randn(G, D, generator=gen)
+    lr = 0.37
+
+    wref = weight.clone().requires_grad_(True)
+    pref = psw.clone().requires_grad_(True) if use_psw else None
+    ref = torch.nn.functional.embedding_bag(slots, wref, offsets, mode=mode, per_sample_weights=pref,
+                                            include_last_offset=True)
+    ref.backward(grad)
+    dense_ref = wref.grad
+    updated_ref = weight - lr * dense_ref
+
+    # sparse COO
+    w = weight.cuda().requires_grad_(True)
+    p = psw.cuda().requires_grad_(True) if use_psw else None
+    out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), p, include_last_offset=True, mode=mode,
+                                  owner=_Owner(sparse=True))
+    out.backward(grad.cuda())
+    assert w.grad.is_sparse
+    torch.testing.assert_close(w.grad.to_dense().cpu(), dense_ref, rtol=1e-4, atol=1e-5)
+    if use_psw:
+        torch.testing.assert_close(p.grad.cpu(), pref.grad, rtol=1e-4, atol=1e-5)
+    # dense
+    w = weight.cuda().requires_grad_(True)
+    out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), psw.cuda() if use_psw else None,
+                                  include_last_offset=True, mode=mode, owner=_Owner(sparse=False))
+    out.backward(grad.cuda())
+    assert not w.grad.is_sparse
+    torch.testing.assert_close(w.grad.cpu(), dense_ref, rtol=1e-4, atol=1e-5)
+    # fused SGD (in place, no grad materialised)
+    w = weight.cuda().requires_grad_(True)
+    fused = {"kind": _lib.OPT_SGD, "lr": lr, "eps": 0.0}
+    out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), psw.cuda() if use_psw else None,
+                                  include_last_offset=True, mode=mode, owner=_Owner(fused=fused))
+    out.backward(grad.cuda())
+    assert w.grad is None
+    torch.testing.assert_close(w.detach().cpu(), updated_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_backward_fused_is_deterministic_and_handles_padding():
+    ce = _mods()
+    from cachedembedding_b200 import _lib
+    gen = torch.Generator().manual_seed(77)
+    C, D, G = 500, 128, 3000
+    weight = torch.randn(C, D, generator=gen)
+    slots, offsets = make_bags(C, D, G, 5, gen)
+    grad = torch.randn(G, D, generator=gen)
+    fused = {"kind": _lib.OPT_SGD, "lr": 0.5, "eps": 0.0}
+    results = []
+    for _ in range(3):
+        w = weight.cuda().requires_grad_(True)
+        out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum",
+                                      padding_idx=7, owner=_Owner(fused=fused))
+        out.backward(grad.cuda())
+        results.append(w.detach().cpu())
+    assert torch.equal(results[0], results[1]) and torch.equal(results[0], results[2]), "fused backward not bitwise repeatable"
+    torch.testing.assert_close(results[0][7], weight[7], rtol=0, atol=0)   # padding slot untouched
+    wref = weight.clone().requires_grad_(True)
+    torch.nn.functional.embedding_bag(slots, wref, offsets, mode="sum", include_last_offset=True,
+                                      padding_idx=7).backward(grad)
+    torch.testing.assert_close(results[0], weight - 0.5 * wref.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("D", [128, 16])
+def test_backward_fused_rowwise_adagrad(D):
+    ce = _mods()
+    from cachedembedding_b200 import _lib
+    gen = torch.Generator().manual_seed(3 + D)
+    C, G = 60, 300
+    weight = torch.randn(C, D, generator=gen)
+    state = torch.rand(C, generator=gen)
+    slots, offsets = make_bags(C, D, G, 4, gen)
+    grad = torch.randn(G, D, generator=gen)
+    lr, eps = 0.1, 1e-8
+    Wref, mref = rowwise_adagrad_reference(weight.numpy(), state.numpy(), slots.numpy(), offsets.numpy(), grad.numpy(),
+                                           lr, eps)
+    w = weight.cuda().requires_grad_(True)
+    st = state.cuda()
+    fused = {"kind": _lib.OPT_ROWWISE_ADAGRAD, "lr": lr, "eps": eps}
+    out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum",
+                                  owner=_Owner(fused=fused, state=st))
+    out.backward(grad.cuda())
+    np.testing.assert_allclose(st.cpu().numpy(), mref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(w.detach().cpu().numpy(), Wref, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- cache manager
+@pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
+@pytest.mark.parametrize("use_freq", [True, False])
+@pytest.mark.parametrize("N,D,ratio,warm", [(1000, 16, 0.1, 0.7), (5000, 128, 0.05, 0.0), (333, 5, 0.3, 1.0)])
+def test_prepare_ids_maps_bit_exact(strategy, use_freq, N, D, ratio, warm):
+    """Slot assignment and every map identical to the oracle after each call, under heavy eviction traffic."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(N + D)
+    weight = torch.randn(N, D, generator=gen)
+    freq = torch.randint(0, 50, (N,), generator=gen) if use_freq else None
+    C = int(N * ratio)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), mode="sum", include_last_offset=True,
+                                  cache_ratio=ratio, ids_freq_mapping=freq, warmup_ratio=warm,
+                                  evict_strategy=getattr(ce.EvictionStrategy, strategy))
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), mode="sum", include_last_offset=True,
+                                      cache_ratio=ratio, ids_freq_mapping=freq, warmup_ratio=warm,
+                                      evict_strategy=getattr(OStrategy, strategy))
+    mgr, omgr = model.cache_weight_mgr, omodel.cache_weight_mgr
+    assert_maps_equal(mgr, omgr)
+    torch.testing.assert_close(mgr.cuda_cached_weight.detach().cpu(), omgr.cuda_cached_weight.detach(), rtol=0, atol=0)
+    for step in range(25):
+        n = int(torch.randint(1, 3 * C, (1,), generator=gen))
+        # zipf-ish ids so that hits, misses, duplicates and ties all occur
+        ids = (torch.rand(n, generator=gen) ** 3 * N).long().clamp_(0, N - 1)
+        if torch.unique(omgr.idx_map[ids]).numel() > C:
+            ids = ids[: C // 2]
+        slots = mgr.prepare_ids(ids.cuda())
+        oslots = omgr.prepare_ids(ids)
+        assert torch.equal(slots.cpu(), oslots), f"slot ids differ at step {step}"
+        assert_maps_equal(mgr, omgr)
+        assert mgr.num_hits_history == omgr.num_hits_history
+        assert mgr.num_miss_history == omgr.num_miss_history
+        assert mgr.num_write_back_history == omgr.num_write_back_history
+        torch.testing.assert_close(mgr.cuda_cached_weight.detach().cpu(), omgr.cuda_cached_weight.detach(),
+                                   rtol=0, atol=0)
+    assert sum(mgr.num_write_back_history) > 0, "the scenario must exercise eviction"
+    assert mgr._cache_miss == omgr._cache_miss and mgr._total_cache == omgr._total_cache
+    mgr.flush()
+    omgr.flush()
+    assert_maps_equal(mgr, omgr)
+    torch.testing.assert_close(mgr.weight, omgr.weight, rtol=0, atol=0)
+
+
+def test_capacity_overflow_leaves_cache_untouched():
+    ce = _mods()
+    model = ce.CachedEmbeddingBag(100, 4, cache_ratio=0.05, evict_strategy=ce.EvictionStrategy.LFU, warmup_ratio=0.4)
+    mgr = model.cache_weight_mgr
+    before = (mgr.cached_idx_map.clone(), mgr.inverted_cached_idx.clone(), mgr.freq_cnter.clone())
+    with pytest.raises(AssertionError, match="increase cuda_row_num or decrease the training batch size"):
+        mgr.prepare_ids(torch.arange(50, 56).cuda())
+    assert torch.equal(before[0], mgr.cached_idx_map) and torch.equal(before[1], mgr.inverted_cached_idx)
+    assert torch.equal(before[2], mgr.freq_cnter)
+    # and the manager still works afterwards
+    s = mgr.prepare_ids(torch.tensor([50, 51, 50]).cuda())
+    assert s[0] == s[2] and s[0] != s[1]
+    with pytest.raises(IndexError):
+        mgr.prepare_ids(torch.tensor([1, 100]).cuda())
+    s = mgr.prepare_ids(torch.tensor([50, 3]).cuda())
+    assert int(mgr.cached_idx_map[s[1]]) == 3
+
+
+def test_cachemgr_kat():  # upstream B.1
+    ce = _mods()
+    model = torch.nn.EmbeddingBag(10000, 128)
+    mgr = ce.CachedParamMgr(model.weight.detach().clone(), 5)
+    assert mgr.cuda_row_num == 5
+    mgr._admit(1)
+    assert not mgr._row_in_cuda(2)
+    assert mgr._row_in_cuda(1)
+    mgr._admit(8)
+    assert mgr.cuda_available_row_num == 3
+    mgr._evict()
+    assert mgr.cuda_available_row_num == 4
+    mgr._prepare_rows_on_cuda(torch.tensor([9, 6, 5], dtype=torch.long, device=0))
+    mgr._prepare_rows_on_cuda(torch.tensor([3, 4, 5], dtype=torch.long, device=0))
+    assert mgr.cuda_available_row_num == 0
+    assert int((mgr.cached_idx_map == 5).sum()) == 1
+    torch.testing.assert_close(mgr.cuda_cached_weight[mgr.inverted_cached_idx[5]].cpu(), model.weight[5].detach())
+    mgr.flush()
+    assert mgr.cuda_available_row_num == 5
+    assert torch.all(mgr.cached_idx_map == -1) and torch.all(mgr.inverted_cached_idx == -1)
+    torch.testing.assert_close(mgr.weight, model.weight.detach(), rtol=0, atol=0)
+
+
+def test_reorder_with_freq_kat():  # upstream B.2
+    ce = _mods()
+    num_embed, num_chunks = 100, 5
+    g = torch.Generator().manual_seed(3)
+    freq = torch.randint(10000, size=(num_embed,), generator=g)
+    sorted_idx = torch.argsort(freq, descending=True, stable=True).tolist()
+    mgr = ce.CachedParamMgr(torch.rand(num_embed, 2), num_chunks)
+    mgr.reorder(freq)
+    got = mgr.idx_map.cpu().tolist()
+    assert got == [sorted_idx.index(i) for i in range(num_embed)]
+
+
+@pytest.mark.parametrize("init_freq", [True, False])
+def test_lfu_strategy_kat(init_freq):  # upstream B.4
+    ce = _mods()
+    Bag = ce.CachedEmbeddingBag(5, 5, cache_ratio=3 / 5, buffer_size=0, pin_weight=True,
+                                ids_freq_mapping=[4, 2, 1, 3, 1] if init_freq else None, warmup_ratio=1.0,
+                                evict_strategy=ce.EvictionStrategy.LFU)
+    offsets = torch.tensor([0], device="cuda:0")
+    seq = [[2], [1, 2], [0, 2]] + [[0, 1, 2]] * 4 + [[0, 2]] * 4 + [[0]] * 4 + \
+          [[0, 1, 2], [0, 1, 2], [3], [2], [4], [2], [0]]
+    for ids in seq:
+        Bag.forward(torch.tensor(ids, device="cuda:0"), offsets)
+    assert Bag.cache_weight_mgr.num_hits_history[-6:] == [3, 0, 1, 0, 1, 1]
+
+
+# ---------------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("use_LFU", [True, False])
+@pytest.mark.parametrize("backward", ["sparse", "fused"])
+def test_freq_aware_embed_matches_full_table(use_LFU, backward):  # upstream B.3, against torch.nn.EmbeddingBag
+    ce = _mods()
+    NUM_EMBED, EMBED_DIM, BATCH = 10, 8, 8
+    gen = torch.Generator().manual_seed(4)
+    strategy = ce.EvictionStrategy.LFU if use_LFU else ce.EvictionStrategy.DATASET
+    model = ce.CachedEmbeddingBag(NUM_EMBED, EMBED_DIM, mode='mean', include_last_offset=True, sparse=True,
+                                  cache_ratio=min(BATCH * 2 / NUM_EMBED, 1.0), ids_freq_mapping=None,
+                                  evict_strategy=strategy)
+    assert model.weight.shape[0] == NUM_EMBED
+    ref_model = torch.nn.EmbeddingBag.from_pretrained(model.weight.detach().clone().cuda(), mode='mean',
+                                                      include_last_offset=True, freeze=False)
+    lr = 1e-3
+    if backward == "fused":
+        model.set_fused_optimizer("sgd", lr=lr)
+    optimizer = torch.optim.SGD(model.parameters(), lr=lr)
+    ref_optimizer = torch.optim.SGD(ref_model.parameters(), lr=lr)
+    for i in range(5):
+        n = BATCH * 2
+        indices = torch.randint(0, NUM_EMBED, (n,), generator=gen).cuda()
+        cuts = torch.sort(torch.randint(1, n, (BATCH - 1,), generator=gen)).values
+        offsets = torch.cat([torch.tensor([0]), cuts, torch.tensor([n])]).cuda()
+        res = model(indices, offsets)
+        ref_res = ref_model(indices, offsets)
+        torch.testing.assert_close(res, ref_res, rtol=RTOL, atol=ATOL)
+        grad = torch.rand(res.shape, generator=gen).cuda()
+        res.backward(grad)
+        ref_res.backward(grad)
+        optimizer.step(); optimizer.zero_grad()
+        ref_optimizer.step(); ref_optimizer.zero_grad()
+    model.cache_weight_mgr.flush()
+    torch.testing.assert_close(model.weight.detach().cuda(), ref_model.weight.detach(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
+def test_training_under_eviction_matches_oracle(strategy):
+    """Several look-ahead windows with fwd + bwd + SGD per batch, cache much smaller than the table: pooled sums,
+    slot ids and the final host table all match the oracle (which itself matches full-table SGD)."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(21)
+    N, D, F, B, P = 4000, 128, 4, 32, 3
+    weight = torch.randn(N, D, generator=gen) * 0.01
+    freq = torch.randint(0, 100, (N,), generator=gen)
+    kw = dict(mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.1, ids_freq_mapping=freq,
+              warmup_ratio=0.7)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(ce.EvictionStrategy, strategy), **kw)
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(OStrategy, strategy), **kw)
+    model.set_fused_optimizer("sgd", lr=0.5)
+    oopt = torch.optim.SGD(omodel.parameters(), lr=0.5)
+    offsets = torch.arange(F * B + 1)
+    for window in range(6):
+        batches = [(torch.rand(F * B, generator=gen) ** 2 * N).long().clamp_(0, N - 1) for _ in range(P)]
+        slots = model.cache_weight_mgr.prepare_ids(torch.cat(batches).cuda())
+        oslots = omodel.cache_weight_mgr.prepare_ids(torch.cat(batches))
+        assert torch.equal(slots.cpu(), oslots)
+        model.set_cache_op(False); omodel.set_cache_op(False)
+        for s, os_ in zip(torch.chunk(slots, P), torch.chunk(oslots, P)):
+            out = model(s, offsets.cuda())
+            oout = omodel(os_, offsets)
+            torch.testing.assert_close(out.cpu(), oout, rtol=RTOL, atol=ATOL)
+            grad = torch.randn(out.shape, generator=gen)
+            out.backward(grad.cuda())
+            oout.backward(grad)
+            oopt.step(); oopt.zero_grad()
+    assert sum(model.num_write_back_history) > 0
+    assert_maps_equal(model.cache_weight_mgr, omodel.cache_weight_mgr)
+    model.cache_weight_mgr.flush(); omodel.cache_weight_mgr.flush()
+    torch.testing.assert_close(model.weight, omodel.weight, rtol=RTOL, atol=ATOL)
+
+
+def test_rowwise_adagrad_state_travels_with_rows():
+    """Row-wise Adagrad through the module with evictions: matches the float64 full-table restatement."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(8)
+    N, D, G = 300, 16, 40
+    weight = torch.randn(N, D, generator=gen)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), mode="sum", include_last_offset=True, sparse=True,
+                                  cache_ratio=0.2, warmup_ratio=0.5, evict_strategy=ce.EvictionStrategy.LFU,
+                                  fused_optimizer="rowwise_adagrad", lr=0.05, eps=1e-8)
+    W, m = weight.numpy().astype(np.float64), np.zeros(N)
+    offsets = torch.arange(G + 1)
+    for _ in range(12):
+        ids = torch.randint(0, N, (G,), generator=gen)
+        grad = torch.randn(G, D, generator=gen)
+        out = model(ids.cuda(), offsets.cuda())
+        out.backward(grad.cuda())
+        W, m = rowwise_adagrad_reference(W, m, ids.numpy(), offsets.numpy(), grad.numpy(), 0.05, 1e-8)
+    assert sum(model.num_write_back_history) > 0
+    model.cache_weight_mgr.flush()
+    np.testing.assert_allclose(model.weight.numpy(), W, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(model.cache_weight_mgr.row_state.numpy(), m, rtol=1e-4, atol=1e-6)
+
+
+def test_module_surface():
+    ce = _mods()
+    model = ce.CachedEmbeddingBag(50, 8, sparse=True, include_last_offset=True,
+                                  evict_strategy=ce.EvictionStrategy.DATASET, cache_ratio=0.5).to(torch.device("cuda:0"))
+    params = list(model.parameters())
+    assert len(params) == 1 and params[0] is model.cache_weight_mgr.cuda_cached_weight
+    assert [n for n, _ in model.named_parameters()] == ["weight"]
+    assert model.weight.device.type == "cpu" and model.weight.shape == (50, 8)
+    assert model.element_size() == 4
+    assert sum(b.numel() for b in model.buffers()) > 0
+    model.set_cache_mgr_async_copy(True)
+    model.zero_grad()
+    model.print_comm_stats_()
+
+
+# ---------------------------------------------------------------------------------------------------- full-size properties
+def test_large_table_round_trip_properties():
+    """BASELINE-scale shapes through size-independent properties (the oracle would take minutes here):
+    (1) cached_idx_map[slot_ids] == idx_map[ids]; (2) every id of the window is resident exactly once;
+    (3) prepare -> flush without updates leaves the host table bit-identical (checksum of checksums);
+    (4) fused SGD with lr=1 and grad g moves the flushed rows by exactly -count*g for a constant grad."""
+    ce = _mods()
+    N, D, B, F = 4_000_000, 128, 65536, 4
+    model = ce.CachedEmbeddingBag(N, D, mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.05,
+                                  warmup_ratio=0.7, evict_strategy=ce.EvictionStrategy.DATASET)
+    mgr = model.cache_weight_mgr
+    before = model.weight.view(-1, 1024).sum(1).clone()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(4):
+        ids = (torch.rand(B * F, generator=gen, device="cuda") ** 4 * N).long().clamp_(0, N - 1)
+        slots = mgr.prepare_ids(ids)
+        assert torch.equal(mgr._slot2row[slots].long(), ids)
+        occ = mgr._slot2row[mgr._slot2row >= 0]
+        assert occ.unique().numel() == occ.numel()
+        assert mgr.cuda_available_row_num + occ.numel() == mgr.cuda_row_num
+    assert sum(mgr.num_write_back_history) > 0
+    mgr.flush()
+    assert torch.equal(model.weight.view(-1, 1024).sum(1), before)
+    # constant-grad linearity
+    model.set_fused_optimizer("sgd", lr=1.0)
+    ids = (torch.rand(B * F, generator=gen, device="cuda") ** 4 * N).long().clamp_(0, N - 1)
+    w0 = model.weight[ids.cpu()[:1000]].clone()
+    counts = torch.bincount(ids, minlength=N)[ids[:1000]].cpu().float()
+    out = model(ids, torch.arange(B * F + 1, device="cuda"))
+    out.backward(torch.full_like(out, 0.25))
+    mgr.flush()
+    torch.testing.assert_close(model.weight[ids.cpu()[:1000]], w0 - 0.25 * counts[:, None], rtol=1e-5, atol=1e-6)
