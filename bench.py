@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- embedding lookups/s (fwd+bwd) of the cached embedding bag on synthetic Criteo-1TB-shape ids.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it is launched under
+torch.distributed.run, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+A "step" is one batch through the hot path: forward (segment-sum gather over the slot cache) + backward fused with
+the SGD update of the cached rows, plus -- once every `prefetch_num` steps -- the cache manager's prepare_ids over the
+whole look-ahead window (id->slot lookup, LFU update, evict/admit, D2H write-back and H2D fill of rows).  This is the
+loop of /root/reference/recsys/dlrm_main.py:235-279 restricted to the embedding operator, i.e. the isolation harness of
+/root/reference/benchmark/benchmark_cache.py:58-72 plus the optimizer step.
+
+Workload at N = 1: BASELINE.json configs[2] -- Criteo-1TB DLRM shape (26 tables, 177,944,275 rows, dim 128, the full
+91.1 GB fp32 table pinned in host DRAM), cache_ratio 0.01, prefetch_num 8, batch 65536 -- whenever the host has the RAM
+for it; otherwise the rows are scaled down and `config.row_scale` says by how much.
+N > 1: the same tables sharded table-wise over the ranks (BASELINE.json configs[3]), global batch 65536, one all-to-all
+of pooled embeddings forward and of their gradients backward ("strong" scaling: total work is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+# /root/reference/recsys/datasets/criteo.py:29-34 (table cardinalities; constants, not code)
+CRITEO_1TB_ROWS = [45833188, 36746, 17245, 7413, 20243, 3, 7114, 1441, 62, 29275261, 1572176, 345138, 10, 2209, 11267,
+                   128, 4, 974, 14, 48937457, 11316796, 40094537, 452104, 12606, 104, 35]
+CRITEO_KAGGLE_ROWS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                      5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+# table -> rank maps of /root/reference/recsys/utils/misc.py:198-206 (criteo 1TB, world 2 and 4); world 8 has no map
+# in the reference, ours is greedy by rows
+REF_RANK_ARRANGE_1TB = {
+    1: [0] * 26,
+    2: [1, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 0, 0, 0],
+    4: [1, 3, 3, 3, 3, 0, 2, 2, 1, 2, 2, 2, 0, 1, 2, 1, 0, 1, 0, 0, 2, 3, 3, 3, 1, 0],
+}
+SKEW = 0.25        # long-tail exponent of the reference's generator (/root/reference/baselines/data/custom.py:23)
+SEED = 1024        # default --seed of the reference (/root/reference/recsys/dlrm_main.py:139-144)
+
+WORKLOADS = {
+    "criteo1tb": dict(rows=CRITEO_1TB_ROWS, dim=128, batch=65536, prefetch=8, cache_ratio=0.01),
+    "kaggle": dict(rows=CRITEO_KAGGLE_ROWS, dim=128, batch=4096, prefetch=8, cache_ratio=0.01),
+    "plumbing": dict(rows=[100000] * 26, dim=16, batch=512, prefetch=1, cache_ratio=0.05),
+}
+
+
+def rank_arrange(rows, world):
+    if world in REF_RANK_ARRANGE_1TB and len(rows) == 26:
+        return REF_RANK_ARRANGE_1TB[world]
+    # greedy: biggest table to the rank with the fewest rows so far, ties to the rank with fewer tables
+    load = [[0, 0, r] for r in range(world)]
+    arrange = [0] * len(rows)
+    for t in sorted(range(len(rows)), key=lambda i: -rows[i]):
+        load.sort(key=lambda x: (x[0], x[1]))
+        arrange[t] = load[0][2]
+        load[0][0] += rows[t]
+        load[0][1] += 1
+    return arrange
+
+
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def sample_ids(rows_dev, batch, gen, device):
+    """One batch of KJT-ordered global ids: values[f*B + b], one id per (feature, sample).
+
+    Per table the reference generator's long tail: idx = floor(u^(-1/s)) - 1, u ~ U[(1/N_f)^s, 1] in float64
+    (/root/reference/baselines/data/custom.py:76,89-91), made global by adding the table's row offset
+    (/root/reference/recsys/datasets/criteo.py:118-119)."""
+    F = rows_dev.numel()
+    n_f = rows_dev.to(torch.float64).view(F, 1)
+    lo = (1.0 / n_f) ** SKEW
+    u = torch.rand(F, batch, dtype=torch.float64, device=device, generator=gen) * (1.0 - lo) + lo
+    idx = torch.floor(u ** (-1.0 / SKEW)).long() - 1
+    idx = torch.minimum(idx.clamp_(min=0), rows_dev.view(F, 1) - 1)
+    offsets = torch.cumsum(rows_dev, 0) - rows_dev
+    return (idx + offsets.view(F, 1)).view(-1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        self.f.close()
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_info():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, local, world
+
+
+# ---------------------------------------------------------------------------------------------------------------- b200
+def run_b200(args):
+    import torch.distributed as dist
+    import cachedembedding_b200 as ce
+    from cachedembedding_b200 import _lib
+    from cachedembedding_b200.collectives import dual_all_to_all_tablewise, split_sizes
+
+    rank, local, world = dist_info()
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = dict(WORKLOADS[args.workload])
+    rows_all = list(wl["rows"])
+    D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
+    # every rank's tables must fit the host: scale rows down only if they do not
+    arrange = rank_arrange(rows_all, world)
+    need_gb = sum(rows_all) * D * 4 / 1e9
+    avail_gb = host_mem_available_gb()
+    row_scale = args.row_scale
+    if row_scale == 0:
+        row_scale = 1
+        while need_gb / row_scale > 0.8 * avail_gb and row_scale < 1024:
+            row_scale *= 2
+    rows_all = [max(1, r // row_scale) for r in rows_all]
+    my_tables = [t for t, r in enumerate(arrange) if r == rank]
+    rows_loc = [rows_all[t] for t in my_tables]
+    F, F_loc = len(rows_all), len(my_tables)
+    N_loc = sum(rows_loc)
+    C_loc = max(int(N_loc * wl["cache_ratio"]), 1)
+    K, W = args.steps, args.warmup
+    total_steps = W + K
+    windows = (total_steps + P - 1) // P
+
+    gen = torch.Generator(device=dev).manual_seed(SEED + rank)
+    rows_dev = torch.tensor(rows_loc, dtype=torch.long, device=dev)
+
+    # id frequencies counted over a sample of the synthetic "dataset" (the reference counts its training set:
+    # /root/reference/recsys/datasets/feature_counter.py:21-29) -> LFU warm start
+    t0 = time.time()
+    freq = torch.zeros(N_loc, dtype=torch.long, device=dev)
+    for _ in range(args.freq_batches):
+        ids = sample_ids(rows_dev, B, gen, dev)
+        freq += torch.bincount(ids, minlength=N_loc)
+    model = ce.CachedEmbeddingBag(N_loc, D, sparse=True, mode="sum", include_last_offset=True,
+                                  cache_ratio=wl["cache_ratio"], ids_freq_mapping=freq, warmup_ratio=0.7,
+                                  evict_strategy=ce.EvictionStrategy.LFU, cuda_row_num=C_loc, init_seed=SEED,
+                                  fused_optimizer="sgd", lr=1.0)
+    del freq
+    mgr = model.cache_weight_mgr
+    model.set_cache_op(False)
+    setup_s = time.time() - t0
+
+    n_b = F_loc * B                         # lookups per step on this rank (pooling factor 1)
+    offsets = torch.arange(n_b + 1, dtype=torch.long, device=dev)
+    # three arms (timed, per-kernel replay, end-to-end) each get their own fresh windows of ids
+    arms = {a: [sample_ids(rows_dev, B, gen, dev) for _ in range(windows * P)] for a in ("value", "profile", "e2e")}
+    # the gradient of the pooled embeddings, fixed (benchmark_cache.py:64); for N > 1 it is what the dense part
+    # returns for this rank's slice of the batch, all features
+    strides = split_sizes(B, world)
+    dim_per_rank = [D * sum(1 for r in arrange if r == q) for q in range(world)]
+    if world > 1:
+        grad_full = torch.randn(strides[rank], F * D, device=dev)
+    else:
+        grad_full = torch.randn(n_b, D, device=dev)
+
+    def embed_step(slots):
+        if world > 1:
+            local_out = model._embed(slots, offsets, None, layout="sample_major", layout_batch=B)
+            out = dual_all_to_all_tablewise(local_out.view(B, F_loc * D), None, strides, dim_per_rank)
+        else:
+            out = model(slots, offsets)
+        out.backward(grad_full)
+        return out
+
+    def run_steps(first, count, host_inputs, batches=None):
+        """Steps [first, first+count).  host_inputs: ids start in pinned host memory and are copied H2D inside the
+        region (the whole window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row is read
+        back D2H per step."""
+        h2d = d2h = 0
+        slots_window = None
+        for s in range(first, first + count):
+            w, j = divmod(s, P)
+            if j == 0 or slots_window is None:
+                if host_inputs:
+                    win = torch.cat([host_batches[w * P + i].to(dev, non_blocking=True) for i in range(P)])
+                    h2d += win.numel() * 8
+                else:
+                    win = torch.cat(batches[w * P:(w + 1) * P])
+                slots_window = torch.chunk(mgr.prepare_ids(win), P)
+            out = embed_step(slots_window[j])
+            if host_inputs:
+                result_host.copy_(out.view(-1)[:D], non_blocking=True)
+                d2h += D * 4
+        return h2d, d2h
+
+    def timed(first, count, host_inputs, batches=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h2d, d2h = run_steps(first, count, host_inputs, batches)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), h2d, d2h
+
+    # ---- device-resident arm: warm-up, then exactly K timed steps -------------------------------------------------
+    # warm-up is rounded to whole windows internally only for the *slot* bookkeeping: steps W..W+K-1 are timed.
+    run_steps(0, W, False, arms["value"])
+    launches0 = _lib.launch_count()
+    hist0 = len(mgr.num_miss_history)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, _, _ = timed(W, K, False, arms["value"])
+    clocks = sampler.stop() if sampler else None
+    gpu_launches = _lib.launch_count() - launches0
+    miss_u = sum(mgr.num_miss_history[hist0:])
+    hit_u = sum(mgr.num_hits_history[hist0:])
+    evicted = sum(mgr.num_write_back_history[hist0:])
+    miss_ratio_lookups = mgr._cache_miss / max(mgr._total_cache, 1)
+
+    # ---- per-kernel timers on a replay of the same steps (CUDA events on the launching stream) ------------------
+    _lib.profile_enable(True)
+    run_steps(W, K, False, arms["profile"])
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+
+    # ---- end-to-end arm: ids come from pinned host memory, one pooled row goes back per step ---------------------
+    host_batches = [b.cpu().pin_memory() for b in arms["e2e"]]
+    result_host = torch.empty(D, dtype=torch.float32).pin_memory()
+    run_steps(0, W, True)
+    e2e_ms, h2d, d2h = timed(W, K, True)
+
+    lookups_per_step = B * F                                  # whole job, all ranks
+    value = lookups_per_step * K / (ms_total / 1e3)
+    e2e_value = lookups_per_step * K / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    uniq = [int(torch.unique(b).numel()) for b in arms["profile"][W:W + min(K, 8)]]
+    u_avg = sum(uniq) / len(uniq)
+    alg = {   # algorithmic bytes per launch
+        "bag_forward": n_b * (8 + 4 * D) + n_b * 4 * D + (n_b + 1) * 8,
+        "bag_backward_phase1": n_b * 4 * D + u_avg * 8 * D + n_b * 8,
+    }
+    kernels = {}
+    for name, (ms, cnt) in prof.items():
+        kernels[name] = {"ms_per_step": ms / K, "launch_groups": cnt}
+        if name in alg and cnt:
+            kernels[name]["achieved_gbs"] = alg[name] / (ms / cnt / 1e3) / 1e9
+    dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_step"])
+    achieved = kernels[dom]["achieved_gbs"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg[dom])}
+
+    line = {
+        "metric": "embedding lookups/sec (fwd+bwd)", "value": value, "unit": "lookups/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
+                        f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
+            "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
+            "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
+            "parallelism": "single GPU" if world == 1 else f"table-wise x{world} + NCCL all-to-all of pooled embeddings",
+            "l2": "inputs larger than L2: each step streams >= 2 x n_b x 512 B (1.7 GB at n_b = 1.7 M) vs 126 MB L2",
+            "unique_rows_per_step": round(u_avg), "unique_hits": hit_u, "unique_misses": miss_u, "evicted_rows": evicted,
+            "miss_ratio_lookups": round(miss_ratio_lookups, 5), "setup_s": round(setup_s, 1),
+        },
+        "roofline": roofline,
+        "kernels": kernels,
+        "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_oracle_arm(args.workload, steps=P, warmup=0, budget_s=40.0)["cpu_baseline"]
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU oracle
+def cpu_oracle_arm(workload, steps, warmup, budget_s=None):
+    """The reference's own CPU implementation of the path = the oracle port (pure-PyTorch ATen ops on host cores; the
+    reference's module itself is third-party, absent, and hard-wired to CUDA buffers).  Every step is one batch of the
+    same shape on a ROW-SCALED table (the ATen op sequence and the ids-per-step are unchanged; the scale is stated)."""
+    from oracle import EvictionStrategy as OStrategy
+    from oracle import OracleCachedEmbeddingBag
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = WORKLOADS[workload]
+    D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
+    scale = 1
+    while sum(wl["rows"]) // scale * D * 4 > 6e9:      # keep the oracle's table under 6 GB
+        scale *= 2
+    rows = [max(1, r // scale) for r in wl["rows"]]
+    N, F = sum(rows), len(rows)
+    gen = torch.Generator().manual_seed(SEED)
+    rows_t = torch.tensor(rows, dtype=torch.long)
+    freq = torch.zeros(N, dtype=torch.long)
+    for _ in range(2):
+        freq += torch.bincount(sample_ids(rows_t, B, gen, "cpu"), minlength=N)
+    model = OracleCachedEmbeddingBag(N, D, sparse=True, mode="sum", include_last_offset=True,
+                                     cache_ratio=wl["cache_ratio"], ids_freq_mapping=freq, warmup_ratio=0.7,
+                                     evict_strategy=OStrategy.LFU,
+                                     _weight=torch.empty(N, D).uniform_(-1.0 / N, 1.0 / N))
+    opt = torch.optim.SGD(model.parameters(), lr=1.0)
+    model.set_cache_op(False)
+    n_b = F * B
+    offsets = torch.arange(n_b + 1)
+    grad = torch.randn(n_b, D)
+    done, step_s, prep_s, preps, slots_window = 0, 0.0, 0.0, 0, None
+    total = warmup + steps
+    for s in range(total):
+        if s % P == 0:
+            batch_ids = [sample_ids(rows_t, B, gen, "cpu") for _ in range(P)]
+            t0 = time.perf_counter()
+            slots_window = torch.chunk(model.cache_weight_mgr.prepare_ids(torch.cat(batch_ids)), P)
+            if s >= warmup:
+                prep_s += time.perf_counter() - t0
+                preps += 1
+        t0 = time.perf_counter()
+        out = model(slots_window[s % P], offsets)
+        out.backward(grad)
+        opt.step()
+        opt.zero_grad()
+        if s >= warmup:
+            step_s += time.perf_counter() - t0
+            done += 1
+            if budget_s is not None and step_s + prep_s > budget_s:
+                break
+    # prepare_ids covers a whole window of P steps: charge each measured step 1/P of the average prepare
+    elapsed = step_s + (prep_s / max(preps, 1)) * (done / P)
+    value = n_b * done / elapsed
+    sample = (f"{done} steps of batch {B} x {F} tables (prefetch window {P}) on the {workload} shape with rows / {scale} "
+              f"({N:,} rows, dim {D}); oracle port = pure-PyTorch CPU ops")
+    return {"value": value, "ms_per_step": elapsed / done * 1e3, "steps": done,
+            "cpu_baseline": {"value": value, "unit": "lookups/s", "cores": cores, "kind": "port", "sample": sample}}
+
+
+def run_reference(args):
+    rank, local, world = dist_info()
+    if rank != 0:
+        return
+    r = cpu_oracle_arm(args.workload, steps=args.steps, warmup=args.warmup, budget_s=args.reference_budget_s)
+    wl = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "embedding lookups/sec (fwd+bwd)", "value": r["value"], "unit": "lookups/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {len(wl['rows'])} tables, dim {wl['dim']}, batch {wl['batch']}, "
+                               f"prefetch_num {wl['prefetch']}, cache_ratio {wl['cache_ratio']}, LFU, SGD lr=1",
+                   "note": "CPU arm: bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": r["cpu_baseline"],
+        "e2e": {"value": r["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="criteo1tb", choices=sorted(WORKLOADS))
+    ap.add_argument("--row-scale", type=int, default=0, help="divide table rows by this (0 = only if the host lacks RAM)")
+    ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

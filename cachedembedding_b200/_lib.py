@@ -25,6 +25,8 @@ FREQ_EMPTY = 2**63 - 1
 # every symbol include/cebag.h declares (tests check the library exports exactly these)
 EXPORTS = (
     "cebag_abi_version", "cebag_last_error",
+    "cebag_launch_count", "cebag_profile_enable", "cebag_profile_num_kernels", "cebag_profile_kernel_name",
+    "cebag_profile_collect",
     "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
     "cebag_host_device_pointer", "cebag_fill_uniform",
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_flush", "cebag_preload",
@@ -81,6 +83,12 @@ _lib = None
 def _declare(lib):
     lib.cebag_abi_version.restype = c_int
     lib.cebag_last_error.restype = c_char_p
+    lib.cebag_launch_count.restype = c_int64
+    lib.cebag_profile_enable.argtypes = [c_int]
+    lib.cebag_profile_num_kernels.restype = c_int
+    lib.cebag_profile_kernel_name.argtypes = [c_int]
+    lib.cebag_profile_kernel_name.restype = c_char_p
+    lib.cebag_profile_collect.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     lib.cebag_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     lib.cebag_host_free.argtypes = [c_void_p]
     lib.cebag_host_register.argtypes = [c_void_p, c_size_t]
@@ -124,6 +132,25 @@ def load():
         raise CebagError(f"libcebag_b200.so ABI {lib.cebag_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    """Kernels launched by the library since it was loaded."""
+    return int(load().cebag_launch_count())
+
+
+def profile_enable(on: bool):
+    check(load().cebag_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """{kernel name: (total ms, launch groups)} since the last collect; waits for the recorded events."""
+    lib = load()
+    k = lib.cebag_profile_num_kernels()
+    ms = (ctypes.c_double * k)()
+    cnt = (c_int64 * k)()
+    check(lib.cebag_profile_collect(ms, cnt))
+    return {lib.cebag_profile_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k) if cnt[i]}
 
 
 def last_error() -> str:

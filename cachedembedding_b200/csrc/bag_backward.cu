@@ -15,6 +15,7 @@
 // (~40 B/lookup).  The same machinery writes a dense [C, D] grad (sparse=False) instead of updating.
 #include "bag_common.cuh"
 #include "radix_sort.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -353,11 +354,14 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     unsigned char* flags = reinterpret_cast<unsigned char*>(ws + L.flags);
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
 
-    bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
-    CEBAG_LAUNCH_CHECK();
-    if (!fast) {
-        lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);
+    {
+        KernelScope scope(kKernBagOf, stream, fast ? 1 : 2);
+        bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
         CEBAG_LAUNCH_CHECK();
+        if (!fast) {
+            lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);
+            CEBAG_LAUNCH_CHECK();
+        }
     }
     const uint32_t *keys = nullptr, *vals = nullptr;
     rc = radix_sort_slots(a->slot_ids, a->n, key_bits_for(a->cache_rows), ws + L.sort,
@@ -373,14 +377,20 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
 #define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
     do {                                                                                                            \
         int grid = grid_for(L.num_chunks * LANES, kBwdThreads, 4);                                                  \
-        if (fast)                                                                                                   \
-            bag_backward_phase1_kernel<VT, LANES, CPL, OPT, true><<<grid, kBwdThreads, 0, stream>>>(                \
-                p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                            \
-        else                                                                                                        \
-            bag_backward_phase1_kernel<VT, LANES, CPL, OPT, false><<<grid, kBwdThreads, 0, stream>>>(               \
-                p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                            \
-        bag_backward_phase2_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(p, up, keys, scratch,     \
-                                                                                          flags, L.num_chunks);     \
+        {                                                                                                           \
+            KernelScope scope1(kKernBwdPhase1, stream);                                                             \
+            if (fast)                                                                                               \
+                bag_backward_phase1_kernel<VT, LANES, CPL, OPT, true><<<grid, kBwdThreads, 0, stream>>>(            \
+                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                        \
+            else                                                                                                    \
+                bag_backward_phase1_kernel<VT, LANES, CPL, OPT, false><<<grid, kBwdThreads, 0, stream>>>(           \
+                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                        \
+        }                                                                                                           \
+        {                                                                                                           \
+            KernelScope scope2(kKernBwdPhase2, stream);                                                             \
+            bag_backward_phase2_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(p, up, keys, scratch, \
+                                                                                              flags, L.num_chunks); \
+        }                                                                                                           \
     } while (0)
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);
 #undef LAUNCH_BWD
@@ -435,6 +445,7 @@ extern "C" int cebag_bag_backward_coo(const cebag_bag_args* a, const float* grad
 #define LAUNCH_COO(VT, LANES, CPL)                                                                 \
     bag_backward_coo_kernel<VT, LANES, CPL><<<grid_for(p.num_bags * LANES, kBwdThreads, 8), kBwdThreads, 0, stream>>>( \
         p, grad_out, values)
+    KernelScope scope(kKernBwdCoo, stream);
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_COO);
 #undef LAUNCH_COO
     CEBAG_LAUNCH_CHECK();
@@ -454,6 +465,7 @@ extern "C" int cebag_bag_backward_weights(const cebag_bag_args* a, const float* 
 #define LAUNCH_GW(VT, LANES, CPL)                                                                  \
     bag_backward_weights_kernel<VT, LANES, CPL><<<grid_for(p.num_bags * LANES, kBwdThreads, 8), kBwdThreads, 0, stream>>>( \
         p, grad_out, grad_weights)
+    KernelScope scope(kKernBwdWeights, stream);
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_GW);
 #undef LAUNCH_GW
     CEBAG_LAUNCH_CHECK();

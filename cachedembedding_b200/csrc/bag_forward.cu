@@ -6,6 +6,7 @@
 // factor 1 (Criteo), each group works on kBagsPerIter consecutive bags at once: all offset loads, then all slot-id
 // loads, then all row loads are issued before any is consumed.
 #include "bag_common.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -148,6 +149,7 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
         int grid = grid_for(groups * LANES, kFwdThreads, 8);                                             \
         bag_forward_kernel<VT, LANES, CPL><<<grid, kFwdThreads, 0, stream>>>(p, out);                    \
     } while (0)
+    KernelScope scope(kKernForward, stream);
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_FWD);
 #undef LAUNCH_FWD
     CEBAG_LAUNCH_CHECK();

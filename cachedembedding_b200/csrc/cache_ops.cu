@@ -18,6 +18,7 @@
 // Integer / byte work throughout; HBM- (maps) and PCIe- (rows) bound.
 #include "common.cuh"
 #include "scan.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -501,8 +502,11 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
     if (t->epoch == 1) CEBAG_CUDA_CHECK(cudaMemsetAsync(t->slot_epoch, 0, (size_t)C * 4, stream));
 
     CEBAG_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * 4, stream));
-    probe_kernel<<<grid_for(ceil_div(n, kProbeIds), kThreads, 8), kThreads, 0, stream>>>(*t, ids, n, slot_ids_out,
-                                                                                        miss_pos, counters);
+    {
+        KernelScope scope(kKernProbe, stream);
+        probe_kernel<<<grid_for(ceil_div(n, kProbeIds), kThreads, 8), kThreads, 0, stream>>>(*t, ids, n, slot_ids_out,
+                                                                                            miss_pos, counters);
+    }
     CEBAG_LAUNCH_CHECK();
     rc = read_counters(counters, host_ctr, stream);
     if (rc) return rc;
@@ -517,10 +521,13 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
     }
     if (miss_lookups > 0) {
         // missed rows, ascending
-        bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums);
-        CEBAG_LAUNCH_CHECK();
-        rc = exclusive_scan_inplace(bitmap_sums, L.bitmap_blocks, counters + kCtrUniqueMisses, scan_ws, stream);
-        if (rc) return rc;
+        {
+            KernelScope scope(kKernBitmapRank, stream);
+            bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums);
+            CEBAG_LAUNCH_CHECK();
+            rc = exclusive_scan_inplace(bitmap_sums, L.bitmap_blocks, counters + kCtrUniqueMisses, scan_ws, stream);
+            if (rc) return rc;
+        }
         rc = read_counters(counters, host_ctr, stream);
         if (rc) return rc;
         const int64_t M = host_ctr[kCtrUniqueMisses];
@@ -532,14 +539,18 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
                       (long long)(stats->unique_hits + M), (long long)C);
             return CEBAG_ERR_CAPACITY;
         }
-        bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
-                                                                              miss_rows, C);
+        {
+            KernelScope scope(kKernBitmapRank, stream);
+            bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
+                                                                                  miss_rows, C);
+        }
         CEBAG_LAUNCH_CHECK();
 
         const int64_t E = M > t->avail ? M - t->avail : 0;
         const int sgrid = grid_for(C, kThreads, 8);
         const bool lfu = t->strategy == CEBAG_EVICT_LFU;
         if (E > 0) {
+            KernelScope scope(kKernSelect, stream, lfu ? 17 : 8);
             SelectState init;
             memset(&init, 0, sizeof(init));
             init.k = E;
@@ -557,26 +568,36 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
                 if (rc) return rc;
             }
         }
-        free_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, sel, (E > 0 && lfu) ? flags_b : nullptr, E > 0 ? 1 : 0,
-                                                          flags_a);
+        {
+            KernelScope scope(kKernFreeSlots, stream, 2);
+            free_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, sel, (E > 0 && lfu) ? flags_b : nullptr,
+                                                              E > 0 ? 1 : 0, flags_a);
+            CEBAG_LAUNCH_CHECK();
+            // flags_b is free again: positions = exclusive scan of the flags
+            CEBAG_CUDA_CHECK(cudaMemcpyAsync(flags_b, flags_a, (size_t)C * 4, cudaMemcpyDeviceToDevice, stream));
+            rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
+            if (rc) return rc;
+            emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(flags_a, flags_b, C, free_slots, M);
+            CEBAG_LAUNCH_CHECK();
+        }
+        {
+            KernelScope scope(kKernSwapRows, stream);
+            const int mgrid = grid_for(M * 32, kThreads, 8);
+            if (table_vec_ok(t)) swap_rows_kernel<true><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
+            else swap_rows_kernel<false><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
+        }
         CEBAG_LAUNCH_CHECK();
-        // flags_b is free again: positions = exclusive scan of the flags
-        CEBAG_CUDA_CHECK(cudaMemcpyAsync(flags_b, flags_a, (size_t)C * 4, cudaMemcpyDeviceToDevice, stream));
-        rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
-        if (rc) return rc;
-        emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(flags_a, flags_b, C, free_slots, M);
-        CEBAG_LAUNCH_CHECK();
-        const int mgrid = grid_for(M * 32, kThreads, 8);
-        if (table_vec_ok(t)) swap_rows_kernel<true><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
-        else swap_rows_kernel<false><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
-        CEBAG_LAUNCH_CHECK();
-        fixup_kernel<<<grid_for(miss_lookups, kThreads, 8), kThreads, 0, stream>>>(*t, ids, miss_pos, miss_lookups,
-                                                                                  slot_ids_out);
+        {
+            KernelScope scope(kKernFixup, stream);
+            fixup_kernel<<<grid_for(miss_lookups, kThreads, 8), kThreads, 0, stream>>>(*t, ids, miss_pos, miss_lookups,
+                                                                                      slot_ids_out);
+        }
         CEBAG_LAUNCH_CHECK();
         stats->evicted = E;
         t->avail += E - M;
     }
     if (t->strategy == CEBAG_EVICT_LFU) {
+        KernelScope scope(kKernLfuCount, stream);
         lfu_count_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, stream>>>(*t, slot_ids_out, n);
         CEBAG_LAUNCH_CHECK();
     }
@@ -591,8 +612,11 @@ extern "C" int cebag_flush(cebag_table* t, const cebag_workspace* ws, int64_t* r
     int32_t* counters = reinterpret_cast<int32_t*>(ws->device);
     CEBAG_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * 4, stream));
     const int grid = grid_for((int64_t)t->cache_rows * 32, kThreads, 8);
-    if (table_vec_ok(t)) flush_kernel<true><<<grid, kThreads, 0, stream>>>(*t, counters);
-    else flush_kernel<false><<<grid, kThreads, 0, stream>>>(*t, counters);
+    {
+        KernelScope scope(kKernFlush, stream);
+        if (table_vec_ok(t)) flush_kernel<true><<<grid, kThreads, 0, stream>>>(*t, counters);
+        else flush_kernel<false><<<grid, kThreads, 0, stream>>>(*t, counters);
+    }
     CEBAG_LAUNCH_CHECK();
     rc = read_counters(counters, reinterpret_cast<int32_t*>(ws->pinned), stream);
     if (rc) return rc;
@@ -611,8 +635,11 @@ extern "C" int cebag_preload(cebag_table* t, const int32_t* rows, const int64_t*
     if (k == 0) return CEBAG_OK;
     CEBAG_REQUIRE(rows != nullptr, "rows");
     const int grid = grid_for(k * 32, kThreads, 8);
-    if (table_vec_ok(t)) move_rows_kernel<true><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
-    else move_rows_kernel<false><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
+    {
+        KernelScope scope(kKernMoveRows, stream);
+        if (table_vec_ok(t)) move_rows_kernel<true><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
+        else move_rows_kernel<false><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
+    }
     CEBAG_LAUNCH_CHECK();
     t->avail -= k;
     return CEBAG_OK;
@@ -624,6 +651,7 @@ extern "C" int cebag_admit_row(cebag_table* t, int64_t row, int64_t slot, void* 
     if (rc) return rc;
     CEBAG_REQUIRE(row >= 0 && row < t->num_rows && slot >= 0 && slot < t->cache_rows, "row / slot");
     CEBAG_REQUIRE(t->avail > 0, "no free slot");
+    count_launches(1);
     move_one_kernel<<<1, 32, 0, stream>>>(*t, (int32_t)row, (int32_t)slot, 0, table_vec_ok(t) ? 1 : 0);
     CEBAG_LAUNCH_CHECK();
     t->avail -= 1;
@@ -635,6 +663,7 @@ extern "C" int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream_) {
     int rc = check_table(t);
     if (rc) return rc;
     CEBAG_REQUIRE(slot >= 0 && slot < t->cache_rows, "slot");
+    count_launches(1);
     move_one_kernel<<<1, 32, 0, stream>>>(*t, -1, (int32_t)slot, 1, table_vec_ok(t) ? 1 : 0);
     CEBAG_LAUNCH_CHECK();
     t->avail += 1;

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -87,6 +88,7 @@ extern "C" int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi,
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CEBAG_REQUIRE(dst != nullptr && count >= 0, "fill_uniform arguments");
     if (count == 0) return CEBAG_OK;
+    KernelScope scope(kKernFill, stream);
     fill_uniform_kernel<<<kNumSMs * 8, 256, 0, stream>>>(dst, count, lo, hi - lo, seed, aligned16(dst) ? 1 : 0);
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "radix_sort.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -145,6 +146,7 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
     int32_t* hist = reinterpret_cast<int32_t*>(ws + L.hist);
     int32_t* scan_ws = reinterpret_cast<int32_t*>(ws + L.scan_ws);
     const int passes = (key_bits + 7) / 8;
+    KernelScope scope(kKernSort, stream, 2 * passes);
     const int bits_per_pass = (key_bits + passes - 1) / passes;
     int shift = 0;
     const void* kin = slot_ids;

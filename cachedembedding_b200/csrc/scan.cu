@@ -2,6 +2,7 @@
 // radix sort's bucket offsets.  Integer-only, HBM/L2-bound; arrays here are small (<= a few M entries).
 #include "common.cuh"
 #include "scan.cuh"
+#include "profile.cuh"
 
 namespace cebag {
 
@@ -77,6 +78,7 @@ int exclusive_scan_inplace(int32_t* data, int64_t len, int32_t* total_out, int32
     }
     if (len <= 16384) {
         scan_single_cta_kernel<<<1, 1024, 0, stream>>>(data, len, total_out);
+        count_launches(1);
         CEBAG_LAUNCH_CHECK();
         return CEBAG_OK;
     }
@@ -87,6 +89,7 @@ int exclusive_scan_inplace(int32_t* data, int64_t len, int32_t* total_out, int32
     scan_single_cta_kernel<<<1, 1024, 0, stream>>>(workspace, chunks, total_out);
     CEBAG_LAUNCH_CHECK();
     chunk_downsweep_kernel<<<(int)chunks, kScanThreads, 0, stream>>>(data, len, workspace);
+    count_launches(3);
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }

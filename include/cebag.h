@@ -93,6 +93,17 @@ typedef struct cebag_prepare_stats {
 CEBAG_API int         cebag_abi_version(void);
 CEBAG_API const char* cebag_last_error(void);
 
+/* ---- launch accounting and per-kernel timers (upstream: CachedParamMgr._elapsed_dict / print_comm_stats) -------
+ * cebag_launch_count: kernels launched by this library since it was loaded.
+ * With profiling enabled every group of launches is bracketed by CUDA events on its stream; cebag_profile_collect
+ * waits for them, fills total_ms[k] / launches[k] for k < cebag_profile_num_kernels() and resets the timers.
+ * Entry k covers the kernels named cebag_profile_kernel_name(k) ("radix_sort" = all kernels of one sort). */
+CEBAG_API int64_t     cebag_launch_count(void);
+CEBAG_API int         cebag_profile_enable(int on);
+CEBAG_API int         cebag_profile_num_kernels(void);
+CEBAG_API const char* cebag_profile_kernel_name(int k);
+CEBAG_API int         cebag_profile_collect(double* total_ms, int64_t* launches);
+
 /* ---- pinned host memory for the table (upstream: weight.pin_memory(), A.1) --------------------------------- */
 CEBAG_API int cebag_host_alloc(void** out_ptr, size_t bytes);                 /* cudaHostAlloc(portable|mapped)          */
 CEBAG_API int cebag_host_free(void* ptr);

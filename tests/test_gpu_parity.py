@@ -12,7 +12,17 @@ pytestmark = pytest.mark.gpu
 from oracle import EvictionStrategy as OStrategy
 from oracle import OracleCachedEmbeddingBag, rowwise_adagrad_reference
 
-RTOL, ATOL = 1e-5, 1e-7   # north_star: 1e-5 relative fp32 (atol covers sums that cancel to ~0)
+# north_star: pooled sums and updated rows within 1e-5 relative fp32.  A sum of several rows that cancels has no
+# meaningful element-wise relative error, so "relative" is taken against the magnitude of the summed operands:
+# |got - want| <= 1e-5 * |want| + 1e-5 * scale, scale = max |operand| (the randn test tables have scale ~4).
+RTOL, ATOL = 1e-5, 4e-5
+
+
+def close(got, want, what=""):
+    """1e-5 relative: element-wise against |want|, plus 1e-5 of the largest magnitude in `want` for sums that cancel."""
+    want = torch.as_tensor(want)
+    got = torch.as_tensor(got).to(want.dtype)
+    torch.testing.assert_close(got, want, rtol=RTOL, atol=RTOL * max(float(want.abs().max()), 1e-30), msg=None)
 
 
 def _mods():
@@ -142,16 +152,16 @@ def test_backward_sparse_dense_and_fused_sgd(D, mode, use_psw):
                                   owner=_Owner(sparse=True))
     out.backward(grad.cuda())
     assert w.grad.is_sparse
-    torch.testing.assert_close(w.grad.to_dense().cpu(), dense_ref, rtol=1e-4, atol=1e-5)
+    close(w.grad.to_dense().cpu(), dense_ref)
     if use_psw:
-        torch.testing.assert_close(p.grad.cpu(), pref.grad, rtol=1e-4, atol=1e-5)
+        close(p.grad.cpu(), pref.grad)
     # dense
     w = weight.cuda().requires_grad_(True)
     out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), psw.cuda() if use_psw else None,
                                   include_last_offset=True, mode=mode, owner=_Owner(sparse=False))
     out.backward(grad.cuda())
     assert not w.grad.is_sparse
-    torch.testing.assert_close(w.grad.cpu(), dense_ref, rtol=1e-4, atol=1e-5)
+    close(w.grad.cpu(), dense_ref)
     # fused SGD (in place, no grad materialised)
     w = weight.cuda().requires_grad_(True)
     fused = {"kind": _lib.OPT_SGD, "lr": lr, "eps": 0.0}
@@ -159,7 +169,7 @@ def test_backward_sparse_dense_and_fused_sgd(D, mode, use_psw):
                                   include_last_offset=True, mode=mode, owner=_Owner(fused=fused))
     out.backward(grad.cuda())
     assert w.grad is None
-    torch.testing.assert_close(w.detach().cpu(), updated_ref, rtol=1e-4, atol=1e-5)
+    close(w.detach().cpu(), updated_ref)
 
 
 def test_backward_fused_is_deterministic_and_handles_padding():
@@ -183,7 +193,7 @@ def test_backward_fused_is_deterministic_and_handles_padding():
     wref = weight.clone().requires_grad_(True)
     torch.nn.functional.embedding_bag(slots, wref, offsets, mode="sum", include_last_offset=True,
                                       padding_idx=7).backward(grad)
-    torch.testing.assert_close(results[0], weight - 0.5 * wref.grad, rtol=1e-4, atol=1e-5)
+    close(results[0], weight - 0.5 * wref.grad)
 
 
 @pytest.mark.parametrize("D", [128, 16])
@@ -205,8 +215,8 @@ def test_backward_fused_rowwise_adagrad(D):
     out = ce.embedding_bag_cached(w, slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum",
                                   owner=_Owner(fused=fused, state=st))
     out.backward(grad.cuda())
-    np.testing.assert_allclose(st.cpu().numpy(), mref, rtol=1e-4, atol=1e-6)
-    np.testing.assert_allclose(w.detach().cpu().numpy(), Wref, rtol=1e-4, atol=1e-5)
+    close(st.cpu().double(), torch.from_numpy(mref))
+    close(w.detach().cpu().double(), torch.from_numpy(Wref))
 
 
 # ---------------------------------------------------------------------------------------------------- cache manager
@@ -410,8 +420,8 @@ def test_rowwise_adagrad_state_travels_with_rows():
         W, m = rowwise_adagrad_reference(W, m, ids.numpy(), offsets.numpy(), grad.numpy(), 0.05, 1e-8)
     assert sum(model.num_write_back_history) > 0
     model.cache_weight_mgr.flush()
-    np.testing.assert_allclose(model.weight.numpy(), W, rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(model.cache_weight_mgr.row_state.numpy(), m, rtol=1e-4, atol=1e-6)
+    close(model.weight.double(), torch.from_numpy(W))
+    close(model.cache_weight_mgr.row_state.double(), torch.from_numpy(m))
 
 
 def test_module_surface():
