@@ -262,12 +262,13 @@ def run_b200(args):
 
     # ---- device-resident arm: warm-up, then exactly K timed steps -------------------------------------------------
     # warm-up is rounded to whole windows internally only for the *slot* bookkeeping: steps W..W+K-1 are timed.
+    # clocks are sampled from the warm-up to the end of the end-to-end arm: every arm runs the same steps, and the
+    # K timed steps alone are shorter than nvidia-smi's sampling period
+    sampler = ClockSampler(local) if rank == 0 else None
     run_steps(0, W, False, arms["value"])
     launches0 = _lib.launch_count()
     hist0 = len(mgr.num_miss_history)
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_total, _, _ = timed(W, K, False, arms["value"])
-    clocks = sampler.stop() if sampler else None
     gpu_launches = _lib.launch_count() - launches0
     miss_u = sum(mgr.num_miss_history[hist0:])
     hit_u = sum(mgr.num_hits_history[hist0:])
@@ -286,6 +287,7 @@ def run_b200(args):
     result_host = torch.empty(D, dtype=torch.float32).pin_memory()
     run_steps(0, W, True)
     e2e_ms, h2d, d2h = timed(W, K, True)
+    clocks = sampler.stop() if sampler else None
 
     lookups_per_step = B * F                                  # whole job, all ranks
     value = lookups_per_step * K / (ms_total / 1e3)
@@ -426,7 +428,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="criteo1tb", choices=sorted(WORKLOADS))

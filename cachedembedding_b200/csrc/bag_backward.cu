@@ -104,109 +104,187 @@ __device__ __forceinline__ void store_partial(float* scratch, int64_t chunk, int
     }
 }
 
+// Phase 1.  A CTA owns a "super-chunk" of G = 256 / LANES consecutive chunks (one group each).  Partial sums of runs
+// that cross a chunk boundary are parked in shared memory and combined inside the CTA, in position order, so only
+// runs that cross a SUPER-chunk boundary leave partials in global memory for phase 2: a slot hit by all 65536
+// lookups of a tiny table leaves 65536 / (G * kChunk) = 128 partials instead of 1024 (LANES = 32).
 // VAL_IS_BAG: sorted values are bag ids and every weight is 1 (mode sum, no per-sample weights)
 template <typename VT, int LANES, int CPL, int OPT, bool VAL_IS_BAG>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
                            const uint32_t* __restrict__ vals, const int32_t* __restrict__ bag_of,
                            const float* __restrict__ wts, const float* __restrict__ grad_out,
-                           float* __restrict__ scratch, unsigned char* __restrict__ flags, int64_t num_chunks) {
+                           float* __restrict__ scratch, unsigned char* __restrict__ flags, int64_t num_chunks,
+                           int64_t num_super) {
+    constexpr int G = kBwdThreads / LANES;
+    __shared__ VT s_part[2][G][LANES * CPL];      // [0] first-run partial, [1] last-run partial of every chunk
+    __shared__ unsigned char s_flag[G];
+    __shared__ uint32_t s_lastkey[G];
+    __shared__ unsigned int s_ctaflag;
     const int lane = threadIdx.x & (LANES - 1);
-    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
-    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int g = threadIdx.x / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
 
-    for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
-        const int64_t start = ck * kChunk;
-        const int64_t end = min(start + (int64_t)kChunk, p.n);
-        bool first_run = true;
-        const bool open_left = start > 0 && keys[start - 1] == keys[start];
+    for (int64_t sc = blockIdx.x; sc < num_super; sc += gridDim.x) {
+        const int64_t ck = sc * G + g;
+        const bool valid = ck < num_chunks;
+        if (threadIdx.x == 0) s_ctaflag = 0;
         unsigned char flag = 0;
-        VT acc[CPL];
+        if (valid) {
+            const int64_t start = ck * kChunk;
+            const int64_t end = min(start + (int64_t)kChunk, p.n);
+            bool first_run = true;
+            const bool open_left = start > 0 && keys[start - 1] == keys[start];
+            VT acc[CPL];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
-        bool pending = false;
+            for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
+            bool pending = false;
 
-        for (int64_t j0 = start; j0 < end; j0 += kUnroll) {
-            uint32_t k[kUnroll];
-            bool live[kUnroll], tail[kUnroll];
-            float w[kUnroll];
-            int64_t grow[kUnroll];
+            for (int64_t j0 = start; j0 < end; j0 += kUnroll) {
+                uint32_t k[kUnroll];
+                bool live[kUnroll], tail[kUnroll];
+                float w[kUnroll];
+                int64_t grow[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                int64_t j = j0 + u;
-                live[u] = j < end;
-                k[u] = live[u] ? keys[j] : 0u;
-                uint32_t knext = (live[u] && j + 1 < p.n) ? keys[j + 1] : ~k[u];
-                tail[u] = live[u] && knext != k[u];
-                uint32_t v = live[u] ? vals[j] : 0u;
-                int64_t bag = VAL_IS_BAG ? (int64_t)v : (live[u] ? (int64_t)bag_of[v] : 0);
-                w[u] = (VAL_IS_BAG || !live[u]) ? 1.f : wts[v];
-                grow[u] = bag_row(p, bag);
-            }
-            VT g[kUnroll][CPL], wr[kUnroll][CPL];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    int col = lane + c * LANES;
-                    bool ok = live[u] && col < chunks;
-                    g[u][c] = ok ? Vec<VT>::ld_stream(gradv + grow[u] * chunks + col) : Vec<VT>::zero();
-                    // current row, needed where a run ends inside this chunk
-                    bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
-                    wr[u][c] = need_row ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)k[u] * chunks + col)
-                                        : Vec<VT>::zero();
+                for (int u = 0; u < kUnroll; ++u) {
+                    int64_t j = j0 + u;
+                    live[u] = j < end;
+                    k[u] = live[u] ? keys[j] : 0u;
+                    uint32_t knext = (live[u] && j + 1 < p.n) ? keys[j + 1] : ~k[u];
+                    tail[u] = live[u] && knext != k[u];
+                    uint32_t v = live[u] ? vals[j] : 0u;
+                    int64_t bag = VAL_IS_BAG ? (int64_t)v : (live[u] ? (int64_t)bag_of[v] : 0);
+                    w[u] = (VAL_IS_BAG || !live[u]) ? 1.f : wts[v];
+                    grow[u] = bag_row(p, bag);
                 }
-            }
+                VT gr[kUnroll][CPL], wr[kUnroll][CPL];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (!live[u]) continue;
+                for (int u = 0; u < kUnroll; ++u) {
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], w[u], g[u][c]);
-                pending = true;
-                if (tail[u]) {
-                    if (first_run && open_left) {
-                        store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
-                        flag |= kFlagOpenLeft;
-                    } else if (k[u] != pad) {
-                        apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, k[u], acc, wr[u]);
+                    for (int c = 0; c < CPL; ++c) {
+                        int col = lane + c * LANES;
+                        bool ok = live[u] && col < chunks;
+                        gr[u][c] = ok ? Vec<VT>::ld_stream(gradv + grow[u] * chunks + col) : Vec<VT>::zero();
+                        // current row, needed where a run ends inside this chunk
+                        bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
+                        wr[u][c] = need_row ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) +
+                                                          (int64_t)k[u] * chunks + col)
+                                            : Vec<VT>::zero();
                     }
+                }
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
-                    first_run = false;
-                    pending = false;
+                for (int u = 0; u < kUnroll; ++u) {
+                    if (!live[u]) continue;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], w[u], gr[u][c]);
+                    pending = true;
+                    if (tail[u]) {
+                        if (first_run && open_left) {
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) s_part[0][g][lane + c * LANES] = acc[c];
+                            flag |= kFlagOpenLeft;
+                        } else if (k[u] != pad) {
+                            apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, k[u], acc, wr[u]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
+                        first_run = false;
+                        pending = false;
+                    }
                 }
             }
+            if (pending) {  // the last run continues into the next chunk
+                if (first_run && open_left) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) s_part[0][g][lane + c * LANES] = acc[c];
+                    flag |= kFlagOpenLeft | kFlagWhole;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) s_part[1][g][lane + c * LANES] = acc[c];
+                    flag |= kFlagOpenRight;
+                }
+            }
+            if (lane == 0) s_lastkey[g] = keys[end - 1];
         }
-        if (pending) {  // the last run continues into the next chunk
-            if (first_run && open_left) {
-                store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
-                flag |= kFlagOpenLeft | kFlagWhole;
-            } else {
-                store_partial<VT, LANES, CPL>(scratch, ck, 1, chunks, lane, acc);
-                flag |= kFlagOpenRight;
+        if (lane == 0) s_flag[g] = flag;
+        __syncthreads();
+
+        // combine inside the CTA, in chunk order
+        const int gvalid = (int)min((int64_t)G, num_chunks - sc * G);
+        if (valid && (flag & kFlagOpenRight)) {          // this chunk holds the head of a run that crosses its end
+            VT acc[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] = s_part[1][g][lane + c * LANES];
+            int h = g + 1;
+            bool ended = false;
+            while (h < gvalid) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, s_part[0][h][lane + c * LANES]);
+                if (!(s_flag[h] & kFlagWhole)) { ended = true; break; }
+                ++h;
+            }
+            const uint32_t slot = s_lastkey[g];
+            if (ended) {
+                if (slot != pad) {
+                    VT wr[CPL];
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        int col = lane + c * LANES;
+                        wr[c] = (col < chunks && OPT != kOptDense)
+                                    ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
+                                    : Vec<VT>::zero();
+                    }
+                    apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
+                }
+            } else {                                      // continues into the next super-chunk
+                store_partial<VT, LANES, CPL>(scratch, sc, 1, chunks, lane, acc);
+                if (lane == 0) atomicOr(&s_ctaflag, (unsigned)kFlagOpenRight);
             }
         }
-        if (lane == 0) flags[ck] = flag;
+        if (g == 0 && (flag & kFlagOpenLeft)) {           // the run that enters this super-chunk from the left
+            VT acc[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] = s_part[0][0][lane + c * LANES];
+            unsigned cf = kFlagOpenLeft;
+            if (flag & kFlagWhole) {
+                int h = 1;
+                bool ended = false;
+                while (h < gvalid) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, s_part[0][h][lane + c * LANES]);
+                    if (!(s_flag[h] & kFlagWhole)) { ended = true; break; }
+                    ++h;
+                }
+                if (!ended) cf |= kFlagWhole;             // one run covers the whole super-chunk and goes on
+            }
+            store_partial<VT, LANES, CPL>(scratch, sc, 0, chunks, lane, acc);
+            if (lane == 0) atomicOr(&s_ctaflag, cf);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) flags[sc] = (unsigned char)s_ctaflag;
+        __syncthreads();
     }
 }
 
+// Phase 2: one group per run that started inside a super-chunk and crossed its end.
 template <typename VT, int LANES, int CPL, int OPT>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase2_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
                            const float* __restrict__ scratch, const unsigned char* __restrict__ flags,
-                           int64_t num_chunks) {
+                           int64_t num_super) {
+    constexpr int G = kBwdThreads / LANES;
+    constexpr int64_t kSuper = (int64_t)G * kChunk;
     const int lane = threadIdx.x & (LANES - 1);
     const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
-    for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
-        if (!(flags[ck] & kFlagOpenRight)) continue;   // only the chunk that holds the head of a crossing run
-        const uint32_t slot = keys[min(ck * kChunk + (int64_t)kChunk, p.n) - 1];
+    for (int64_t ck = group; ck < num_super; ck += num_groups) {
+        if (!(flags[ck] & kFlagOpenRight)) continue;   // only the super-chunk that holds the head of a crossing run
+        const uint32_t slot = keys[min((ck + 1) * kSuper, p.n) - 1];
         VT acc[CPL], wr[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -216,17 +294,37 @@ bag_backward_phase2_kernel(const BagParams p, const UpdateParams up, const uint3
                         ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
                         : Vec<VT>::zero();
         }
-        for (int64_t c2 = ck + 1; c2 < num_chunks; ++c2) {
-            unsigned char f = flags[c2];
+        // the run continues through every following super-chunk flagged Whole and ends in the first one that is
+        // not; partials are added in order (deterministic), kBatch loads in flight at a time
+        constexpr int kBatch = 8;
+        int64_t c2 = ck + 1;
+        bool more = c2 < num_super;
+        while (more) {
+            int take = 0;
+            while (take < kBatch && c2 + take < num_super) {
+                unsigned char f = flags[c2 + take];
+                ++take;
+                if (!(f & kFlagWhole)) { more = false; break; }
+            }
+            if (c2 + take >= num_super) more = false;
+            VT part[kBatch][CPL];
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                int col = lane + c * LANES;
-                if (col < chunks) {
-                    VT part = Vec<VT>::ld(sv + (c2 * 2) * chunks + col);
-                    Vec<VT>::fma(acc[c], 1.f, part);
+            for (int b = 0; b < kBatch; ++b) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    int col = lane + c * LANES;
+                    part[b][c] = (b < take && col < chunks) ? Vec<VT>::ld(sv + ((c2 + b) * 2) * chunks + col)
+                                                            : Vec<VT>::zero();
                 }
             }
-            if (!(f & kFlagWhole)) break;
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                if (b < take) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, part[b][c]);
+                }
+            }
+            c2 += take;
         }
         if (slot != pad) apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
     }
@@ -311,6 +409,9 @@ struct BwdLayout {
     size_t sort, bag_of, wts, scratch, flags, total;
     int64_t num_chunks;
 };
+// super-chunks for a group width: G = kBwdThreads / lanes chunks each; the layout is sized for the narrowest group
+// (lanes = 32 -> G = 8), which has the most super-chunks
+static inline int64_t num_super_for(int64_t num_chunks, int lanes) { return ceil_div(num_chunks, kBwdThreads / lanes); }
 
 BwdLayout bwd_layout(int64_t n, int dim) {
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -321,8 +422,9 @@ BwdLayout bwd_layout(int64_t n, int dim) {
     L.sort = off; off += align(radix_sort_workspace_bytes(nn));
     L.bag_of = off; off += align((size_t)nn * 4);
     L.wts = off; off += align((size_t)nn * 4);
-    L.scratch = off; off += align((size_t)L.num_chunks * 2 * dim * 4);
-    L.flags = off; off += align((size_t)L.num_chunks);
+    const int64_t max_super = num_super_for(L.num_chunks, 32);
+    L.scratch = off; off += align((size_t)max_super * 2 * dim * 4);
+    L.flags = off; off += align((size_t)max_super);
     L.total = off;
     return L;
 }
@@ -376,20 +478,22 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     up.dim = a->dim;
 #define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
     do {                                                                                                            \
-        int grid = grid_for(L.num_chunks * LANES, kBwdThreads, 4);                                                  \
+        const int64_t num_super = num_super_for(L.num_chunks, LANES);                                               \
         {                                                                                                           \
             KernelScope scope1(kKernBwdPhase1, stream);                                                             \
+            int grid = (int)(num_super < (int64_t)kNumSMs * 8 ? num_super : (int64_t)kNumSMs * 8);                  \
             if (fast)                                                                                               \
                 bag_backward_phase1_kernel<VT, LANES, CPL, OPT, true><<<grid, kBwdThreads, 0, stream>>>(            \
-                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                        \
+                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super);             \
             else                                                                                                    \
                 bag_backward_phase1_kernel<VT, LANES, CPL, OPT, false><<<grid, kBwdThreads, 0, stream>>>(           \
-                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks);                        \
+                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super);             \
         }                                                                                                           \
         {                                                                                                           \
             KernelScope scope2(kKernBwdPhase2, stream);                                                             \
+            int grid = grid_for(num_super * LANES, kBwdThreads, 4);                                                 \
             bag_backward_phase2_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(p, up, keys, scratch, \
-                                                                                              flags, L.num_chunks); \
+                                                                                              flags, num_super);    \
         }                                                                                                           \
     } while (0)
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);

@@ -378,16 +378,22 @@ fixup_kernel(const cebag_table t, const int64_t* __restrict__ ids, const int32_t
     }
 }
 
+// LFU counters += multiplicity.  A warp whose 32 ids share one slot (tiny tables, feature-major ids) adds 32 with one
+// atomic; otherwise every lane issues its own fire-and-forget reduction.
 __global__ void __launch_bounds__(kThreads)
 lfu_count_kernel(const cebag_table t, const int64_t* __restrict__ slots, int64_t n) {
     const int lane = lane_id();
     const int64_t span = ((n + 31) / 32) * 32;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < span; i += (int64_t)gridDim.x * kThreads) {
-        bool live = i < n;
-        long long s = live ? slots[i] : -1 - (long long)lane;   // dead lanes match only themselves
-        unsigned peers = __match_any_sync(0xffffffffu, s);
-        if (live && lane == __ffs(peers) - 1)
-            atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s), (unsigned long long)__popc(peers));
+        const bool live = i < n;
+        const long long s = live ? slots[i] : -1;
+        int same = 0;
+        __match_all_sync(0xffffffffu, s, &same);
+        if (same) {
+            if (live && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s), 32ull);
+        } else if (live) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s), 1ull);
+        }
     }
 }
 

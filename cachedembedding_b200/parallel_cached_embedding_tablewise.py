@@ -110,24 +110,32 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
     def split_along_rank(self, batch_size, indices: torch.Tensor, offsets: torch.Tensor = None,
                          per_sample_weights=None):
         """Cut this rank's tables out of a global KJT (values = global ids, feature-major offsets)."""
-        li, lo, lw = [], [], []
-        pre_end = 0
-        # table boundaries on the host once (upstream does .item() per table)
-        bounds = offsets[torch.arange(0, offsets.shape[0], batch_size, device=offsets.device)].tolist()
-        for k, t in enumerate(self.assigned_table_list):
-            start = bounds[t]
-            if (not self.include_last_offset) and batch_size * (t + 1) >= offsets.shape[0]:
-                end = indices.shape[0]
-            else:
-                end = bounds[t + 1]
-            li.append(indices.narrow(0, start, end - start) - self.idx_offset_list[k])
-            if per_sample_weights is not None:
-                lw.append(per_sample_weights.narrow(0, start, end - start))
-            last = (k + 1 == len(self.assigned_table_list))
-            take = batch_size + 1 if (last and self.include_last_offset) else batch_size
-            lo.append(offsets.narrow(0, batch_size * t, take) + (pre_end - start))
-            pre_end += end - start
-        return (torch.cat(li), torch.cat(lo), torch.cat(lw) if per_sample_weights is not None else None)
+        return split_kjt_along_rank(self.assigned_table_list, self.idx_offset_list, self.include_last_offset,
+                                    batch_size, indices, offsets, per_sample_weights)
 
     def set_cache_op(self, cache_op: bool = True):
         self.cache_op = cache_op
+
+
+def split_kjt_along_rank(assigned_table_list, idx_offset_list, include_last_offset, batch_size, indices, offsets,
+                         per_sample_weights=None):
+    """Host logic of upstream's split_along_rank (A.6): slice the id ranges of the local tables out of a global KJT
+    (feature-major: bag g = table * batch_size + sample), re-base the ids by `idx_offset_list` and rebuild the local
+    offsets.  Table boundaries are read back once (upstream does one .item() per table)."""
+    li, lo, lw = [], [], []
+    pre_end = 0
+    bounds = offsets[torch.arange(0, offsets.shape[0], batch_size, device=offsets.device)].tolist()
+    for k, t in enumerate(assigned_table_list):
+        start = bounds[t]
+        if (not include_last_offset) and batch_size * (t + 1) >= offsets.shape[0]:
+            end = indices.shape[0]
+        else:
+            end = bounds[t + 1]
+        li.append(indices.narrow(0, start, end - start) - idx_offset_list[k])
+        if per_sample_weights is not None:
+            lw.append(per_sample_weights.narrow(0, start, end - start))
+        last = (k + 1 == len(assigned_table_list))
+        take = batch_size + 1 if (last and include_last_offset) else batch_size
+        lo.append(offsets.narrow(0, batch_size * t, take) + (pre_end - start))
+        pre_end += end - start
+    return (torch.cat(li), torch.cat(lo), torch.cat(lw) if per_sample_weights is not None else None)

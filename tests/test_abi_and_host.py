@@ -1,0 +1,154 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cebag.h declares (no compute calls),
+host logic of the parallel bags, and the world_size-2 exchange over gloo."""
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "cebag.h")).read()
+    return sorted(set(re.findall(r"CEBAG_API\s+[\w\s\*]+?\b(cebag_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cachedembedding_b200 import _lib
+    lib = _lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 20
+    assert sorted(_lib.EXPORTS) == declared, "binding and header disagree"
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cebag_abi_version() == _lib.ABI_VERSION
+    # the library's own symbol table holds nothing else with the cebag_ prefix
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T cebag_" in l)
+    assert exported == declared
+
+
+def test_no_cpu_fallback():
+    import cachedembedding_b200 as ce
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ce.CachedParamMgr(torch.zeros(8, 4), 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ce.embedding_bag_cached(torch.zeros(4, 4), torch.zeros(2, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cachedembedding_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.parametrize("D,W", [(128, 8), (10, 4), (7, 3), (16, 1)])
+def test_get_partition_is_tensor_split(D, W):
+    from cachedembedding_b200 import get_partition
+    from oracle import get_partition as oget
+    chunks = torch.tensor_split(torch.arange(D), W)
+    for r in range(W):
+        s, e, div = get_partition(D, r, W)
+        assert (s, e) == (int(chunks[r][0]), int(chunks[r][-1]) + 1)
+        assert (s, e, div) == oget(D, r, W)
+
+
+def test_split_kjt_along_rank_matches_oracle():
+    from cachedembedding_b200.parallel_cached_embedding_tablewise import split_kjt_along_rank
+    from oracle import OracleTablewiseConfig, OracleTablewiseWorld
+    gen = torch.Generator().manual_seed(0)
+    rows = [6, 5, 7, 3]
+    ranks = [0, 1, 0, 1]
+    cfgs = [OracleTablewiseConfig(n, 0, assigned_rank=r, initial_weight=torch.rand(n, 4)) for n, r in zip(rows, ranks)]
+    for include_last in (True, False):
+        world = OracleTablewiseWorld(cfgs, 4, 2, include_last_offset=include_last, cache_ratio=1.0)
+        B = 5
+        lens = torch.randint(0, 4, (len(rows) * B,), generator=gen)
+        offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(lens, 0)])
+        goff = torch.cumsum(torch.tensor([0] + rows), 0)
+        ids = torch.cat([torch.randint(0, rows[t], (int(lens[t * B:(t + 1) * B].sum()),), generator=gen) + goff[t]
+                         for t in range(len(rows))])
+        psw = torch.rand(ids.numel(), generator=gen)
+        offs = offsets if include_last else offsets[:-1]
+        for rk in range(2):
+            want = world.split_along_rank(rk, B, ids, offs, psw)
+            got = split_kjt_along_rank(world.assigned[rk], world.idx_offset_list[rk], include_last, B, ids, offs, psw)
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
+
+
+def test_bench_placement_and_sampler():
+    import bench
+    for W in (1, 2, 4, 8):
+        arr = bench.rank_arrange(bench.CRITEO_1TB_ROWS, W)
+        assert len(arr) == 26 and set(arr) == set(range(W))
+    rows = torch.tensor([1000, 3, 50])
+    ids = bench.sample_ids(rows, 4096, torch.Generator().manual_seed(1), "cpu").view(3, 4096)
+    assert int(ids[0].min()) >= 0 and int(ids[0].max()) < 1000
+    assert int(ids[1].min()) >= 1000 and int(ids[1].max()) < 1003
+    assert int(ids[2].min()) >= 1003 and int(ids[2].max()) < 1053
+    # long tail: row 0 of a table is by far the most frequent
+    assert (ids[0] == 0).float().mean() > 0.15
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _exchange_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cachedembedding_b200.collectives import dual_all_to_all, dual_all_to_all_tablewise, split_sizes
+    torch.manual_seed(0)
+    B, D = 5, 3                       # B not divisible by the world: remainder goes to the low ranks
+    dim_per_rank = [2 * D, 1 * D]     # rank 0 owns two tables, rank 1 one
+    locals_ = [torch.arange(B * d, dtype=torch.float32).view(B, d) + 100 * r for r, d in enumerate(dim_per_rank)]
+    x = locals_[rank].clone().requires_grad_(True)
+    strides = split_sizes(B, world)
+    out = dual_all_to_all_tablewise(x, None, strides, dim_per_rank)
+    begin = sum(strides[:rank])
+    want = torch.cat([l[begin:begin + strides[rank]] for l in locals_], 1)
+    ok = torch.equal(out.detach(), want)
+    # backward: grad of rank j's output rows flows back to every rank's local columns
+    grads = [torch.arange(strides[j] * sum(dim_per_rank), dtype=torch.float32).view(strides[j], -1) * (j + 1)
+             for j in range(world)]
+    out.backward(grads[rank])
+    col0 = sum(dim_per_rank[:rank])
+    want_g = torch.cat([g[:, col0:col0 + dim_per_rank[rank]] for g in grads], 0)
+    ok = ok and torch.equal(x.grad, want_g)
+    # column-wise exchange: scatter rows, gather columns of unequal width
+    widths = [2, 1]
+    shard = (torch.arange(6 * widths[rank], dtype=torch.float32).view(6, widths[rank]) + 10 * rank).requires_grad_(True)
+    full = dual_all_to_all(shard, None, 0, -1, fwd_gather_sizes=widths, bwd_gather_sizes=split_sizes(6, world))
+    shards = [torch.arange(6 * w, dtype=torch.float32).view(6, w) + 10 * r for r, w in enumerate(widths)]
+    want_full = torch.cat([torch.tensor_split(s, world, 0)[rank] for s in shards], -1)
+    ok = ok and torch.equal(full.detach(), want_full)
+    full.sum().backward()
+    ok = ok and torch.equal(shard.grad, torch.ones_like(shard))
+    results[rank] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_to_all_exchange_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, results), nprocs=world, join=True)
+    assert all(results[r] for r in range(world)), dict(results)
