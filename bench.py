@@ -177,7 +177,8 @@ def run_b200(args):
     rows_loc = [rows_all[t] for t in my_tables]
     F, F_loc = len(rows_all), len(my_tables)
     N_loc = sum(rows_loc)
-    C_loc = max(int(N_loc * wl["cache_ratio"]), 1)
+    # slots follow the UNSCALED table (a window of the full batch must still fit when rows are scaled down)
+    C_loc = min(N_loc, max(int(sum(wl["rows"][t] for t in my_tables) * wl["cache_ratio"]), 1))
     K, W = args.steps, args.warmup
     total_steps = W + K
     windows = (total_steps + P - 1) // P
@@ -202,6 +203,7 @@ def run_b200(args):
     setup_s = time.time() - t0
 
     n_b = F_loc * B                         # lookups per step on this rank (pooling factor 1)
+    overlap = not args.no_overlap
     offsets = torch.arange(n_b + 1, dtype=torch.long, device=dev)
     # three arms (timed, per-kernel replay, end-to-end) each get their own fresh windows of ids
     arms = {a: [sample_ids(rows_dev, B, gen, dev) for _ in range(windows * P)] for a in ("value", "profile", "e2e")}
@@ -223,25 +225,41 @@ def run_b200(args):
         out.backward(grad_full)
         return out
 
+    def window_ids(w, host_inputs, batches):
+        src = host_batches if host_inputs else batches
+        return src[w * P:(w + 1) * P]
+
     def run_steps(first, count, host_inputs, batches=None):
         """Steps [first, first+count).  host_inputs: ids start in pinned host memory and are copied H2D inside the
-        region (the whole window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row is read
-        back D2H per step."""
+        region (every batch of a window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row is
+        read back D2H per step.  With overlap the prepare_ids of window w+1 runs on a side stream under window w."""
         h2d = d2h = 0
-        slots_window = None
-        for s in range(first, first + count):
-            w, j = divmod(s, P)
-            if j == 0 or slots_window is None:
-                if host_inputs:
-                    win = torch.cat([host_batches[w * P + i].to(dev, non_blocking=True) for i in range(P)])
-                    h2d += win.numel() * 8
-                else:
-                    win = torch.cat(batches[w * P:(w + 1) * P])
+        last = first + count
+        w_first, w_last = first // P, (last - 1) // P
+        pf = ce.LookaheadPrefetcher(model) if overlap else None
+        handle = pf.submit(window_ids(w_first, host_inputs, batches)) if overlap else None
+        for w in range(w_first, w_last + 1):
+            if overlap:
+                slots_window = torch.chunk(handle.wait(), P)
+            else:
+                win = torch.cat([b.to(dev, non_blocking=True) for b in window_ids(w, host_inputs, batches)])
                 slots_window = torch.chunk(mgr.prepare_ids(win), P)
-            out = embed_step(slots_window[j])
             if host_inputs:
-                result_host.copy_(out.view(-1)[:D], non_blocking=True)
-                d2h += D * 4
+                h2d += P * n_b * 8
+            for j in range(P):
+                s = w * P + j
+                if s < first or s >= last:
+                    continue
+                out = embed_step(slots_window[j])
+                if host_inputs:
+                    result_host.copy_(out.view(-1)[:D], non_blocking=True)
+                    d2h += D * 4
+            if overlap:
+                pf.window_enqueued()
+                if w < w_last:
+                    handle = pf.submit(window_ids(w + 1, host_inputs, batches))
+        if overlap:
+            pf.close()
         return h2d, d2h
 
     def timed(first, count, host_inputs, batches=None):
@@ -323,6 +341,7 @@ def run_b200(args):
         "config": {
             "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
                         f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
+            "lookahead": "prepare_ids(window k+1) on a side stream under window k" if overlap else "serial (reference order)",
             "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
             "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
             "parallelism": "single GPU" if world == 1 else f"table-wise x{world} + NCCL all-to-all of pooled embeddings",
@@ -435,6 +454,7 @@ def main():
     ap.add_argument("--row-scale", type=int, default=0, help="divide table rows by this (0 = only if the host lacks RAM)")
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="prepare_ids on the compute stream (reference order)")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:

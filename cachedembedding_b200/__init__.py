@@ -11,11 +11,12 @@ from .cached_embedding import (CachedEmbeddingBag, FreqAwareEmbeddingBag, BaseEm
                                alloc_pinned_table)
 from .parallel_cached_embedding import ParallelCachedEmbeddingBag
 from .parallel_cached_embedding_tablewise import ParallelCachedEmbeddingBagTablewise
+from .lookahead import LookaheadPrefetcher, PrefetchHandle
 from .collectives import dual_all_to_all, dual_all_to_all_tablewise, get_partition
 
 __all__ = [
     'EvictionStrategy', 'TablewiseEmbeddingBagConfig', 'LimitBuffIndexCopyer', 'CachedParamMgr', 'CacheCapacityError',
     'CachedEmbeddingBag', 'FreqAwareEmbeddingBag', 'BaseEmbeddingBag', 'embedding_bag_cached', 'alloc_pinned_table',
     'ParallelCachedEmbeddingBag', 'ParallelCachedEmbeddingBagTablewise', 'dual_all_to_all',
-    'dual_all_to_all_tablewise', 'get_partition',
+    'dual_all_to_all_tablewise', 'get_partition', 'LookaheadPrefetcher', 'PrefetchHandle',
 ]

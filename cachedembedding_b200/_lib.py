@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
@@ -47,6 +47,7 @@ class CacheCapacityError(AssertionError, CebagError):
 class Table(Structure):
     _fields_ = [
         ("num_rows", c_int64), ("dim", c_int32), ("cache_rows", c_int32), ("strategy", c_int32), ("epoch", c_int32),
+        ("protect_windows", c_int32), ("reserved0", c_int32),
         ("avail", c_int64),
         ("host_table", c_void_p), ("host_state", c_void_p), ("cache", c_void_p), ("cache_state", c_void_p),
         ("idx_map", c_void_p), ("row2slot", c_void_p), ("slot2row", c_void_p), ("freq", c_void_p),

@@ -123,6 +123,7 @@ class CachedParamMgr(nn.Module):
             self._state_pin = None
             self.cuda_cached_state = None
         self._epoch = 0
+        self.protect_windows = 1      # 2 while a LookaheadPrefetcher overlaps prepare_ids with the previous window
         self._counters_pinned = torch.zeros(64, dtype=torch.int32).pin_memory()
 
         self.evict_backlist = torch.tensor([], device=dev)
@@ -143,6 +144,7 @@ class CachedParamMgr(nn.Module):
         t.cache_rows = self.cuda_row_num
         t.strategy = _lib.EVICT_LFU if self._evict_strategy == EvictionStrategy.LFU else _lib.EVICT_DATASET
         t.epoch = self._epoch
+        t.protect_windows = self.protect_windows
         t.avail = self._cuda_available_row_num
         t.host_table = self._pin.device_ptr
         t.host_state = self._state_pin.device_ptr if self._state_pin is not None else None

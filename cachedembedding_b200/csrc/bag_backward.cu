@@ -23,7 +23,6 @@ namespace {
 
 constexpr int kBwdThreads = 256;
 constexpr int kChunk = 64;       // sorted positions per group
-constexpr int kUnroll = 4;       // positions in flight per group
 
 enum : int { kOptSgd = 0, kOptAdagrad = 1, kOptDense = 2 };
 enum : unsigned char { kFlagOpenLeft = 1, kFlagOpenRight = 2, kFlagWhole = 4 };
@@ -109,7 +108,7 @@ __device__ __forceinline__ void store_partial(float* scratch, int64_t chunk, int
 // runs that cross a SUPER-chunk boundary leave partials in global memory for phase 2: a slot hit by all 65536
 // lookups of a tiny table leaves 65536 / (G * kChunk) = 128 partials instead of 1024 (LANES = 32).
 // VAL_IS_BAG: sorted values are bag ids and every weight is 1 (mode sum, no per-sample weights)
-template <typename VT, int LANES, int CPL, int OPT, bool VAL_IS_BAG>
+template <typename VT, int LANES, int CPL, int OPT, bool VAL_IS_BAG, int kUnroll>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
                            const uint32_t* __restrict__ vals, const int32_t* __restrict__ bag_of,
@@ -476,18 +475,25 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     up.lr = lr;
     up.eps = eps;
     up.dim = a->dim;
+    // sorted positions in flight per group (tunable: CEBAG_BWD_UNROLL = 4 | 8; 8 only for one chunk per lane)
+    static const int unroll_env = env_int("CEBAG_BWD_UNROLL", 4);
+    static const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 8);
+#define LAUNCH_P1(VT, LANES, CPL, FAST, UNROLL)                                                                     \
+    bag_backward_phase1_kernel<VT, LANES, CPL, OPT, FAST, UNROLL><<<grid, kBwdThreads, 0, stream>>>(                \
+        p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super)
 #define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
     do {                                                                                                            \
         const int64_t num_super = num_super_for(L.num_chunks, LANES);                                               \
         {                                                                                                           \
             KernelScope scope1(kKernBwdPhase1, stream);                                                             \
-            int grid = (int)(num_super < (int64_t)kNumSMs * 8 ? num_super : (int64_t)kNumSMs * 8);                  \
-            if (fast)                                                                                               \
-                bag_backward_phase1_kernel<VT, LANES, CPL, OPT, true><<<grid, kBwdThreads, 0, stream>>>(            \
-                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super);             \
-            else                                                                                                    \
-                bag_backward_phase1_kernel<VT, LANES, CPL, OPT, false><<<grid, kBwdThreads, 0, stream>>>(           \
-                    p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super);             \
+            const int64_t cap = (int64_t)kNumSMs * bwd_ctas_per_sm;                                                 \
+            int grid = (int)(num_super < cap ? num_super : cap);                                                    \
+            if (fast) {                                                                                             \
+                if (unroll_env >= 8 && CPL == 1) LAUNCH_P1(VT, LANES, CPL, true, 8);                                \
+                else LAUNCH_P1(VT, LANES, CPL, true, 4);                                                            \
+            } else {                                                                                                \
+                LAUNCH_P1(VT, LANES, CPL, false, 4);                                                                \
+            }                                                                                                       \
         }                                                                                                           \
         {                                                                                                           \
             KernelScope scope2(kKernBwdPhase2, stream);                                                             \
@@ -498,6 +504,7 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     } while (0)
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);
 #undef LAUNCH_BWD
+#undef LAUNCH_P1
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }

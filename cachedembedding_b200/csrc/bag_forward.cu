@@ -13,9 +13,8 @@ namespace cebag {
 namespace {
 
 constexpr int kFwdThreads = 256;
-constexpr int kBagsPerIter = 4;
 
-template <typename VT, int LANES, int CPL>
+template <typename VT, int LANES, int CPL, int kBagsPerIter>
 __global__ void __launch_bounds__(kFwdThreads)
 bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int lane = threadIdx.x & (LANES - 1);
@@ -143,15 +142,26 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     BagParams p;
     int rc = fill_bag_params(a, &p, rs);
     if (rc) return rc;
+    // bags in flight per group: 8 / CPL by default (tunable: CEBAG_FWD_BPI = 2 | 4 | 8)
+    static const int bpi_env = env_int("CEBAG_FWD_BPI", 0);
+    static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 8);
+#define LAUNCH_FWD_BPI(VT, LANES, CPL, BPI)                                                              \
+    do {                                                                                                 \
+        int64_t groups = ceil_div(p.num_bags, BPI);                                                      \
+        int grid = grid_for(groups * LANES, kFwdThreads, ctas_per_sm);                                   \
+        bag_forward_kernel<VT, LANES, CPL, BPI><<<grid, kFwdThreads, 0, stream>>>(p, out);               \
+    } while (0)
 #define LAUNCH_FWD(VT, LANES, CPL)                                                                       \
     do {                                                                                                 \
-        int64_t groups = ceil_div(p.num_bags, kBagsPerIter);                                             \
-        int grid = grid_for(groups * LANES, kFwdThreads, 8);                                             \
-        bag_forward_kernel<VT, LANES, CPL><<<grid, kFwdThreads, 0, stream>>>(p, out);                    \
+        int bpi = bpi_env ? bpi_env : (CPL == 1 ? 8 : CPL == 2 ? 4 : 2);                                 \
+        if (bpi >= 8 && CPL == 1) LAUNCH_FWD_BPI(VT, LANES, CPL, 8);                                     \
+        else if (bpi >= 4 && CPL <= 2) LAUNCH_FWD_BPI(VT, LANES, CPL, 4);                                \
+        else LAUNCH_FWD_BPI(VT, LANES, CPL, 2);                                                          \
     } while (0)
     KernelScope scope(kKernForward, stream);
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_FWD);
 #undef LAUNCH_FWD
+#undef LAUNCH_FWD_BPI
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }

@@ -28,6 +28,7 @@ constexpr int kThreads = 256;
 
 // counters read back by the host (int32 each)
 enum : int { kCtrUniqueHits = 0, kCtrMissLookups = 1, kCtrBadIndex = 2, kCtrUniqueMisses = 3, kCtrFlushed = 4,
+             kCtrEvictable = 5,
              kNumCounters = 16 };
 
 struct SelectState {             // radix-select of the k smallest keys
@@ -144,10 +145,25 @@ bitmap_emit_kernel(const uint32_t* __restrict__ bitmap, int64_t words, const int
 // ---- victim selection ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, unsigned long long* key) {
     int32_t row = t.slot2row[s];
-    if (row < 0 || t.slot_epoch[s] == t.epoch) return false;        // empty, or needed by this window
+    if (row < 0) return false;                                       // empty
+    const int32_t stamp = t.slot_epoch[s];
+    if (stamp != 0 && t.epoch - stamp < t.protect_windows) return false;   // needed by a protected window
     if (t.strategy == CEBAG_EVICT_LFU) *key = (unsigned long long)t.freq[s];   // smallest counter first
     else *key = (unsigned long long)(0xffffffffu - (uint32_t)row);             // largest row first
     return true;
+}
+
+// how many occupied slots may be evicted (only needed when more than the current window is protected)
+__global__ void __launch_bounds__(kThreads)
+count_evictable_kernel(const cebag_table t, int32_t* __restrict__ counters) {
+    int32_t c = 0;
+    for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < t.cache_rows; s += (int64_t)gridDim.x * kThreads) {
+        unsigned long long key;
+        c += slot_key(t, s, &key) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane_id() == 0 && c) atomicAdd(&counters[kCtrEvictable], c);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -442,6 +458,7 @@ int check_table(const cebag_table* t) {
     CEBAG_REQUIRE(t->host_table && t->cache && t->row2slot && t->slot2row && t->slot_epoch && t->miss_bitmap,
                   "table pointers");
     CEBAG_REQUIRE(t->strategy != CEBAG_EVICT_LFU || t->freq != nullptr, "LFU needs freq");
+    CEBAG_REQUIRE(t->protect_windows >= 1 && t->protect_windows <= 1024, "protect_windows");
     return CEBAG_OK;
 }
 
@@ -554,6 +571,23 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
 
         const int64_t E = M > t->avail ? M - t->avail : 0;
         const int sgrid = grid_for(C, kThreads, 8);
+        if (E > 0 && t->protect_windows > 1) {
+            // rows of an earlier, still protected window cannot be victims: make sure enough others exist
+            count_evictable_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters);
+            count_launches(1);
+            CEBAG_LAUNCH_CHECK();
+            rc = read_counters(counters, host_ctr, stream);
+            if (rc) return rc;
+            if (E > host_ctr[kCtrEvictable]) {
+                clear_bitmap();
+                set_error("You move %lld embedding rows from CPU to CUDA while %d look-ahead windows are protected: only "
+                          "%lld of the %lld cached rows may be evicted but %lld are needed. It is larger than the capacity "
+                          "of the cache, Please increase cuda_row_num or decrease the training batch size.",
+                          (long long)(stats->unique_hits + M), t->protect_windows, (long long)host_ctr[kCtrEvictable],
+                          (long long)C, (long long)E);
+                return CEBAG_ERR_CAPACITY;
+            }
+        }
         const bool lfu = t->strategy == CEBAG_EVICT_LFU;
         if (E > 0) {
             KernelScope scope(kKernSelect, stream, lfu ? 17 : 8);

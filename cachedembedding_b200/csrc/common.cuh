@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/cebag.h"
 
 namespace cebag {
@@ -72,6 +73,12 @@ __device__ __forceinline__ void add4(float4& acc, const float4& v) {
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// integer tuning knob from the environment (read once by the callers)
+static inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

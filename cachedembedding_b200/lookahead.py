@@ -1,0 +1,94 @@
+"""Look-ahead driver: prepare_ids of window k+1 overlaps the forward/backward of window k.
+
+The reference gathers `prefetch_num` batches, runs ONE prepare_ids over their concatenated ids and only then steps
+through them (/root/reference/recsys/dlrm_main.py:245-266); every cache operation is serialised with compute (its
+timers end in torch.cuda.synchronize()).  Here the cache operation of the NEXT window -- id->slot
+probe, victim selection, the PCIe row swap, LFU update -- runs on a high-priority side stream while the compute stream
+works through the current window.
+
+Hazards and how they are closed:
+  * rows the in-flight window k still reads/updates must not be evicted by prepare(k+1): the manager protects the
+    slots stamped by the last TWO windows (`protect_windows = 2`); the capacity rule becomes
+    |rows(k) U rows(k+1)| <= cuda_row_num, checked before anything is changed;
+  * a victim may have been updated by window k-1's backward: the side stream waits for the event recorded after
+    window k-1's compute was enqueued;
+  * slot ids are produced on the side stream and consumed on the compute stream: `Handle.wait()` makes the compute
+    stream wait for the prepare's completion event and records the cross-stream use.
+Pooled sums and updated rows are unaffected by which victims are chosen (the cache is transparent); the slot maps
+follow the oracle run with the same two-window protection (tests/test_gpu_parity.py).
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Optional
+
+import torch
+
+
+class PrefetchHandle:
+    def __init__(self, slot_ids: torch.Tensor, done: torch.cuda.Event):
+        self._slot_ids = slot_ids
+        self._done = done
+
+    def wait(self) -> torch.Tensor:
+        """Slot ids of the window; the current stream waits (on the device) for the cache operation to finish."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._done)
+        self._slot_ids.record_stream(cur)
+        return self._slot_ids
+
+
+class LookaheadPrefetcher:
+    """
+    pf = LookaheadPrefetcher(bag)
+    h = pf.submit(ids_of_window_0)
+    for k in range(num_windows):
+        slot_ids = h.wait()
+        ... forward / backward of the window's batches with bag.set_cache_op(False) ...
+        pf.window_enqueued()
+        if k + 1 < num_windows:
+            h = pf.submit(ids_of_window_k_plus_1)      # overlaps the work just enqueued
+    pf.close()
+    """
+
+    def __init__(self, bag_or_mgr, priority: int = -1):
+        self.mgr = getattr(bag_or_mgr, "cache_weight_mgr", bag_or_mgr)
+        self.device = self.mgr.device
+        self.stream = torch.cuda.Stream(device=self.device, priority=priority)
+        self._fences = deque(maxlen=2)     # events after the compute of the last two windows
+        self._saved_protect = self.mgr.protect_windows
+        self.mgr.protect_windows = max(2, self.mgr.protect_windows)
+
+    def submit(self, ids) -> PrefetchHandle:
+        """Enqueue prepare_ids(ids) on the side stream.  `ids` is a tensor or a list of tensors (the batches of the
+        window, concatenated here like recsys/dlrm_main.py:259 does); they may live in (pinned) host memory, in which
+        case the H2D copies run on the side stream as well."""
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)                          # ids produced on the current stream are complete
+        side = self.stream
+        side.wait_event(ready)
+        if len(self._fences) == 2:
+            side.wait_event(self._fences[0])       # window k-1 finished: its updates are in the rows we may evict
+        with torch.cuda.stream(side):
+            parts = ids if isinstance(ids, (list, tuple)) else [ids]
+            parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
+            ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
+            slot_ids = self.mgr.prepare_ids(ids_dev)
+            done = torch.cuda.Event()
+            done.record(side)
+        for t in parts:
+            if t.is_cuda:
+                t.record_stream(side)
+        return PrefetchHandle(slot_ids, done)
+
+    def window_enqueued(self):
+        """Call after the forward/backward of the current window has been enqueued on the compute stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._fences.append(ev)
+
+    def close(self):
+        """Back to the reference's one-window protection (waits for the side stream)."""
+        self.stream.synchronize()
+        self.mgr.protect_windows = self._saved_protect

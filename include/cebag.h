@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 1
+#define CEBAG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -60,6 +60,10 @@ typedef struct cebag_table {
     int32_t   cache_rows;     /* C: slots in HBM                                                          */
     int32_t   strategy;       /* CEBAG_EVICT_*                                                            */
     int32_t   epoch;          /* window stamp, advanced by every prepare_ids (library-maintained)         */
+    int32_t   protect_windows;/* slots stamped by the last `protect_windows` prepare_ids calls are never evicted:
+                                 1 = the reference's rule (only the current call's rows, A.4);
+                                 2 = look-ahead overlap: the previous window may still be computing on them    */
+    int32_t   reserved0;
     int64_t   avail;          /* free slots (library-maintained; upstream _cuda_available_row_num)        */
     float*    host_table;     /* fp32[N, D]  pinned host memory, device-visible address                   */
     float*    host_state;     /* fp32[N]     row-wise Adagrad state in pinned host memory, or NULL        */

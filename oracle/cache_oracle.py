@@ -86,6 +86,9 @@ class OracleCachedParamMgr(nn.Module):
             self.register_buffer("freq_cnter", torch.full((cuda_row_num,), _MAXSIZE, dtype=torch.long),
                                  persistent=False)
         self.evict_backlist = torch.tensor([], dtype=torch.long)
+        # look-ahead extension (not in the reference): rows of the previous prepare_ids call stay protected too
+        self.protect_windows = 1
+        self._prev_rows = torch.tensor([], dtype=torch.long)
         self.num_hits_history: List[int] = []
         self.num_miss_history: List[int] = []
         self.num_write_back_history: List[int] = []
@@ -148,6 +151,7 @@ class OracleCachedParamMgr(nn.Module):
         self._cuda_available_row_num += slots.numel()
         if self._evict_strategy == EvictionStrategy.LFU:
             self.freq_cnter.fill_(_MAXSIZE)
+        self._prev_rows = torch.tensor([], dtype=torch.long)
         assert self._cuda_available_row_num == self.cuda_row_num
         assert torch.all(self.inverted_cached_idx == -1).item()
         assert torch.all(self.cached_idx_map == -1).item()
@@ -166,7 +170,7 @@ class OracleCachedParamMgr(nn.Module):
             f"You move {len(cpu_row_idxs)} embedding rows from CPU to CUDA. " \
             f"It is larger than the capacity of the cache, which at most contains {self.cuda_row_num} rows, " \
             f"Please increase cuda_row_num or decrease the training batch size."
-        self.evict_backlist = cpu_row_idxs
+        self.evict_backlist = cpu_row_idxs if self.protect_windows == 1 else torch.cat([cpu_row_idxs, self._prev_rows])
         miss_mask = torch.isin(cpu_row_idxs, self.cached_idx_map, invert=True)
         comm_cpu_row_idxs = cpu_row_idxs[miss_mask]
         self._cache_miss += int(repeat_times[miss_mask].sum().item())
@@ -176,6 +180,7 @@ class OracleCachedParamMgr(nn.Module):
         self.num_write_back_history.append(0)
         self._prepare_rows_on_cuda(comm_cpu_row_idxs)
         self.evict_backlist = torch.tensor([], dtype=cpu_row_idxs.dtype)
+        self._prev_rows = cpu_row_idxs
         gpu_row_idxs = self._id_to_cached_cuda_id(ids)
         if self._evict_strategy == EvictionStrategy.LFU:
             unique_gpu_row_idxs = self.inverted_cached_idx[cpu_row_idxs]
@@ -200,6 +205,11 @@ class OracleCachedParamMgr(nn.Module):
         if evict_num > 0:
             mask_cpu_row_idx = torch.isin(self.cached_idx_map, self.evict_backlist)
             invalid_idxs = torch.nonzero(mask_cpu_row_idx).squeeze(1)
+            evictable = int((self.cached_idx_map >= 0).sum()) - invalid_idxs.numel()
+            assert evict_num <= evictable, \
+                f"only {evictable} cached rows may be evicted but {evict_num} are needed: " \
+                f"Please increase cuda_row_num or decrease the training batch size."
+
             if self._evict_strategy == EvictionStrategy.DATASET:
                 backup_idxs = self.cached_idx_map[mask_cpu_row_idx].clone()
                 self.cached_idx_map.index_fill_(0, invalid_idxs, -2)

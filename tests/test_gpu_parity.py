@@ -439,6 +439,70 @@ def test_module_surface():
     model.print_comm_stats_()
 
 
+# ---------------------------------------------------------------------------------------------------- look-ahead overlap
+@pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
+def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy):
+    """prepare_ids of window k+1 on a side stream while window k trains: slot ids and maps bit-exact against the
+    oracle run with the same two-window protection; pooled sums / final table within 1e-5 of it."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(33)
+    N, D, F, B, P = 6000, 128, 4, 64, 2
+    weight = torch.randn(N, D, generator=gen) * 0.01
+    freq = torch.randint(0, 100, (N,), generator=gen)
+    kw = dict(mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.25, ids_freq_mapping=freq,
+              warmup_ratio=0.7)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(ce.EvictionStrategy, strategy), **kw)
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(OStrategy, strategy), **kw)
+    omodel.cache_weight_mgr.protect_windows = 2
+    model.set_fused_optimizer("sgd", lr=0.5)
+    model.set_cache_op(False); omodel.set_cache_op(False)
+    oopt = torch.optim.SGD(omodel.parameters(), lr=0.5)
+    offsets = torch.arange(F * B + 1)
+    windows = [[(torch.rand(F * B, generator=gen) ** 2 * N).long().clamp_(0, N - 1) for _ in range(P)] for _ in range(8)]
+    grads = [[torch.randn(F * B, D, generator=gen) for _ in range(P)] for _ in range(8)]
+    pf = ce.LookaheadPrefetcher(model)
+    assert model.cache_weight_mgr.protect_windows == 2
+    h = pf.submit(torch.cat(windows[0]).pin_memory())          # host ids: the H2D copy rides the side stream too
+    for k in range(len(windows)):
+        slots = h.wait()
+        oslots = omodel.cache_weight_mgr.prepare_ids(torch.cat(windows[k]))
+        outs = []
+        for s, g in zip(torch.chunk(slots, P), grads[k]):
+            out = model(s, offsets.cuda())
+            out.backward(g.cuda())
+            outs.append(out)
+        pf.window_enqueued()
+        if k + 1 < len(windows):
+            h = pf.submit(torch.cat(windows[k + 1]).cuda())
+        assert torch.equal(slots.cpu(), oslots), f"slot ids differ in window {k}"
+        for s, g, out in zip(torch.chunk(oslots, P), grads[k], outs):
+            oout = omodel(s, offsets)
+            close(out.cpu(), oout.detach())
+            oout.backward(g)
+            oopt.step(); oopt.zero_grad()
+    pf.close()
+    assert model.cache_weight_mgr.protect_windows == 1
+    assert sum(model.num_write_back_history) > 0
+    # the oracle is one prepare behind in wall-clock order only; the maps agree once both have seen every window
+    assert_maps_equal(model.cache_weight_mgr, omodel.cache_weight_mgr)
+    model.cache_weight_mgr.flush(); omodel.cache_weight_mgr.flush()
+    close(model.weight, omodel.weight)
+
+
+def test_two_window_protection_capacity_error():
+    ce = _mods()
+    model = ce.CachedEmbeddingBag(100, 4, cache_ratio=0.1, warmup_ratio=0.0, evict_strategy=ce.EvictionStrategy.LFU)
+    mgr = model.cache_weight_mgr
+    mgr.protect_windows = 2
+    mgr.prepare_ids(torch.arange(0, 6).cuda())
+    mgr.prepare_ids(torch.arange(10, 14).cuda())             # fills the cache: 6 + 4 rows
+    with pytest.raises(AssertionError, match="increase cuda_row_num or decrease the training batch size"):
+        mgr.prepare_ids(torch.arange(20, 27).cuda())         # needs 7 victims, only 6 are unprotected
+    assert int((mgr.cached_idx_map >= 0).sum()) == 10
+    s = mgr.prepare_ids(torch.arange(20, 25).cuda())         # 5 victims fit
+    assert torch.equal(mgr.cached_idx_map[s].cpu(), torch.arange(20, 25))
+
+
 # ---------------------------------------------------------------------------------------------------- full-size properties
 def test_large_table_round_trip_properties():
     """BASELINE-scale shapes through size-independent properties (the oracle would take minutes here):
