@@ -22,7 +22,8 @@ namespace cebag {
 namespace {
 
 constexpr int kBwdThreads = 256;
-constexpr int kChunk = 64;       // sorted positions per group
+constexpr int kChunk = 64;        // sorted positions per group
+constexpr int kSuperChunks = 16;  // chunks per super-chunk (phase 2a)
 
 enum : int { kOptSgd = 0, kOptAdagrad = 1, kOptDense = 2 };
 enum : unsigned char { kFlagOpenLeft = 1, kFlagOpenRight = 2, kFlagWhole = 4 };
@@ -103,74 +104,127 @@ __device__ __forceinline__ void store_partial(float* scratch, int64_t chunk, int
     }
 }
 
-// Phase 1.  A CTA owns a "super-chunk" of G = 256 / LANES consecutive chunks (one group each).  Partial sums of runs
-// that cross a chunk boundary are parked in shared memory and combined inside the CTA, in position order, so only
-// runs that cross a SUPER-chunk boundary leave partials in global memory for phase 2: a slot hit by all 65536
-// lookups of a tiny table leaves 65536 / (G * kChunk) = 128 partials instead of 1024 (LANES = 32).
+// Adds the parked first-run partials of elements h, h+1, ... (chunks or super-chunks) to `acc`, in order, while each
+// element is flagged Whole (one run covers it entirely and continues); the first element that is not Whole is added
+// too and closes the run.  kBatch loads are in flight at a time.  Returns true when the run closed inside [h, hend).
+template <typename VT, int LANES, int CPL>
+__device__ __forceinline__ bool chain_sum(const VT* __restrict__ sv, const unsigned char* __restrict__ flags,
+                                          int64_t h, int64_t hend, int chunks, int lane, VT (&acc)[CPL]) {
+    constexpr int kBatch = 8;
+    bool ended = false;
+    while (!ended && h < hend) {
+        int take = 0;
+        while (take < kBatch && h + take < hend) {
+            unsigned char f = flags[h + take];
+            ++take;
+            if (!(f & kFlagWhole)) { ended = true; break; }
+        }
+        VT part[kBatch][CPL];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                int col = lane + c * LANES;
+                part[b][c] = (b < take && col < chunks) ? Vec<VT>::ld(sv + ((h + b) * 2) * chunks + col) : Vec<VT>::zero();
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            if (b < take) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, part[b][c]);
+            }
+        }
+        h += take;
+    }
+    return ended;
+}
+
+template <typename VT, int LANES, int CPL, int OPT>
+__device__ __forceinline__ void load_row_and_apply(const UpdateParams& up, int chunks, int lane, uint32_t slot,
+                                                   const VT (&acc)[CPL]) {
+    VT wr[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int col = lane + c * LANES;
+        wr[c] = (col < chunks && OPT != kOptDense)
+                    ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
+                    : Vec<VT>::zero();
+    }
+    apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
+}
+
+// Phase 1: one group per chunk of kChunk sorted positions; groups are independent (no block-level barrier).
+// The group reads its (slot, value) pairs LANES at a time with coalesced loads (lane l owns position sb + l and also
+// looks at the next key, which tells it whether a run ends there), then walks them kUnroll at a time with shuffles:
+// the grad rows -- and the cached row wherever a run ends -- of kUnroll positions are loaded back to back.
 // VAL_IS_BAG: sorted values are bag ids and every weight is 1 (mode sum, no per-sample weights)
 template <typename VT, int LANES, int CPL, int OPT, bool VAL_IS_BAG, int kUnroll>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
                            const uint32_t* __restrict__ vals, const int32_t* __restrict__ bag_of,
                            const float* __restrict__ wts, const float* __restrict__ grad_out,
-                           float* __restrict__ scratch, unsigned char* __restrict__ flags, int64_t num_chunks,
-                           int64_t num_super) {
-    constexpr int G = kBwdThreads / LANES;
-    __shared__ VT s_part[2][G][LANES * CPL];      // [0] first-run partial, [1] last-run partial of every chunk
-    __shared__ unsigned char s_flag[G];
-    __shared__ uint32_t s_lastkey[G];
-    __shared__ unsigned int s_ctaflag;
+                           float* __restrict__ scratch, unsigned char* __restrict__ flags, int64_t num_chunks) {
     const int lane = threadIdx.x & (LANES - 1);
-    const int g = threadIdx.x / LANES;
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane_id() & ~(LANES - 1)));
+    const int gshift = lane_id() & ~(LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
+    const VT* __restrict__ cachev = reinterpret_cast<const VT*>(up.cache);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
 
-    for (int64_t sc = blockIdx.x; sc < num_super; sc += gridDim.x) {
-        const int64_t ck = sc * G + g;
-        const bool valid = ck < num_chunks;
-        if (threadIdx.x == 0) s_ctaflag = 0;
+    for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
+        const int64_t start = ck * kChunk;
+        const int64_t end = min(start + (int64_t)kChunk, p.n);
+        bool first_run = true;
+        const bool open_left = start > 0 && keys[start - 1] == keys[start];
         unsigned char flag = 0;
-        if (valid) {
-            const int64_t start = ck * kChunk;
-            const int64_t end = min(start + (int64_t)kChunk, p.n);
-            bool first_run = true;
-            const bool open_left = start > 0 && keys[start - 1] == keys[start];
-            VT acc[CPL];
+        VT acc[CPL];
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
-            bool pending = false;
+        for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
+        bool pending = false;
 
-            for (int64_t j0 = start; j0 < end; j0 += kUnroll) {
+#pragma unroll 1
+        for (int64_t sb = start; sb < end; sb += LANES) {
+            const int64_t pos = sb + lane;
+            const bool mine = pos < end;
+            const uint32_t my_key = mine ? keys[pos] : 0u;
+            const uint32_t my_next = (mine && pos + 1 < p.n) ? keys[pos + 1] : ~my_key;
+            const uint32_t my_val = mine ? vals[pos] : 0u;
+            const int my_bag = VAL_IS_BAG ? (int)my_val : (mine ? bag_of[my_val] : 0);
+            const float my_w = (VAL_IS_BAG || !mine) ? 1.f : wts[my_val];
+            const int my_grow = (int)bag_row(p, my_bag);
+            const unsigned tailbits = __ballot_sync(gmask, mine && my_next != my_key) >> gshift;
+            const int nl = (int)min((int64_t)LANES, end - sb);
+
+#pragma unroll 1
+            for (int u0 = 0; u0 < nl; u0 += kUnroll) {
                 uint32_t k[kUnroll];
-                bool live[kUnroll], tail[kUnroll];
+                int grow[kUnroll];
                 float w[kUnroll];
-                int64_t grow[kUnroll];
+                bool live[kUnroll], tail[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    int64_t j = j0 + u;
-                    live[u] = j < end;
-                    k[u] = live[u] ? keys[j] : 0u;
-                    uint32_t knext = (live[u] && j + 1 < p.n) ? keys[j + 1] : ~k[u];
-                    tail[u] = live[u] && knext != k[u];
-                    uint32_t v = live[u] ? vals[j] : 0u;
-                    int64_t bag = VAL_IS_BAG ? (int64_t)v : (live[u] ? (int64_t)bag_of[v] : 0);
-                    w[u] = (VAL_IS_BAG || !live[u]) ? 1.f : wts[v];
-                    grow[u] = bag_row(p, bag);
+                    const int src = min(u0 + u, LANES - 1);
+                    live[u] = u0 + u < nl;
+                    k[u] = __shfl_sync(gmask, my_key, src, LANES);
+                    grow[u] = __shfl_sync(gmask, my_grow, src, LANES);
+                    w[u] = VAL_IS_BAG ? 1.f : __shfl_sync(gmask, my_w, src, LANES);
+                    tail[u] = live[u] && ((tailbits >> (u0 + u)) & 1u);
                 }
                 VT gr[kUnroll][CPL], wr[kUnroll][CPL];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
-                        int col = lane + c * LANES;
-                        bool ok = live[u] && col < chunks;
-                        gr[u][c] = ok ? Vec<VT>::ld_stream(gradv + grow[u] * chunks + col) : Vec<VT>::zero();
+                        const int col = lane + c * LANES;
+                        const bool ok = live[u] && col < chunks;
+                        gr[u][c] = ok ? Vec<VT>::ld_stream(gradv + (int64_t)grow[u] * chunks + col) : Vec<VT>::zero();
                         // current row, needed where a run ends inside this chunk
-                        bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
-                        wr[u][c] = need_row ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) +
-                                                          (int64_t)k[u] * chunks + col)
-                                            : Vec<VT>::zero();
+                        const bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
+                        wr[u][c] = need_row ? Vec<VT>::ld(cachev + (int64_t)k[u] * chunks + col) : Vec<VT>::zero();
                     }
                 }
 #pragma unroll
@@ -181,8 +235,7 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                     pending = true;
                     if (tail[u]) {
                         if (first_run && open_left) {
-#pragma unroll
-                            for (int c = 0; c < CPL; ++c) s_part[0][g][lane + c * LANES] = acc[c];
+                            store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
                             flag |= kFlagOpenLeft;
                         } else if (k[u] != pad) {
                             apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, k[u], acc, wr[u]);
@@ -194,138 +247,100 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                     }
                 }
             }
-            if (pending) {  // the last run continues into the next chunk
-                if (first_run && open_left) {
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) s_part[0][g][lane + c * LANES] = acc[c];
-                    flag |= kFlagOpenLeft | kFlagWhole;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) s_part[1][g][lane + c * LANES] = acc[c];
-                    flag |= kFlagOpenRight;
-                }
-            }
-            if (lane == 0) s_lastkey[g] = keys[end - 1];
         }
-        if (lane == 0) s_flag[g] = flag;
-        __syncthreads();
-
-        // combine inside the CTA, in chunk order
-        const int gvalid = (int)min((int64_t)G, num_chunks - sc * G);
-        if (valid && (flag & kFlagOpenRight)) {          // this chunk holds the head of a run that crosses its end
-            VT acc[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] = s_part[1][g][lane + c * LANES];
-            int h = g + 1;
-            bool ended = false;
-            while (h < gvalid) {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, s_part[0][h][lane + c * LANES]);
-                if (!(s_flag[h] & kFlagWhole)) { ended = true; break; }
-                ++h;
-            }
-            const uint32_t slot = s_lastkey[g];
-            if (ended) {
-                if (slot != pad) {
-                    VT wr[CPL];
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) {
-                        int col = lane + c * LANES;
-                        wr[c] = (col < chunks && OPT != kOptDense)
-                                    ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
-                                    : Vec<VT>::zero();
-                    }
-                    apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
-                }
-            } else {                                      // continues into the next super-chunk
-                store_partial<VT, LANES, CPL>(scratch, sc, 1, chunks, lane, acc);
-                if (lane == 0) atomicOr(&s_ctaflag, (unsigned)kFlagOpenRight);
+        if (pending) {  // the last run continues into the next chunk
+            if (first_run && open_left) {
+                store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
+                flag |= kFlagOpenLeft | kFlagWhole;
+            } else {
+                store_partial<VT, LANES, CPL>(scratch, ck, 1, chunks, lane, acc);
+                flag |= kFlagOpenRight;
             }
         }
-        if (g == 0 && (flag & kFlagOpenLeft)) {           // the run that enters this super-chunk from the left
-            VT acc[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] = s_part[0][0][lane + c * LANES];
-            unsigned cf = kFlagOpenLeft;
-            if (flag & kFlagWhole) {
-                int h = 1;
-                bool ended = false;
-                while (h < gvalid) {
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, s_part[0][h][lane + c * LANES]);
-                    if (!(s_flag[h] & kFlagWhole)) { ended = true; break; }
-                    ++h;
-                }
-                if (!ended) cf |= kFlagWhole;             // one run covers the whole super-chunk and goes on
-            }
-            store_partial<VT, LANES, CPL>(scratch, sc, 0, chunks, lane, acc);
-            if (lane == 0) atomicOr(&s_ctaflag, cf);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) flags[sc] = (unsigned char)s_ctaflag;
-        __syncthreads();
+        if (lane == 0) flags[ck] = flag;
     }
 }
 
-// Phase 2: one group per run that started inside a super-chunk and crossed its end.
+// Phase 2a: one group per super-chunk of kSuperChunks chunks.  Runs that crossed chunk boundaries but end inside
+// the super-chunk are finished here; a run that enters from the left / leaves to the right leaves ONE partial per
+// super-chunk, so a slot hit by all 65536 lookups of a tiny table is a chain of 64 partials in phase 2b, not 1024.
 template <typename VT, int LANES, int CPL, int OPT>
 __global__ void __launch_bounds__(kBwdThreads)
-bag_backward_phase2_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
-                           const float* __restrict__ scratch, const unsigned char* __restrict__ flags,
-                           int64_t num_super) {
-    constexpr int G = kBwdThreads / LANES;
-    constexpr int64_t kSuper = (int64_t)G * kChunk;
+bag_backward_phase2a_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
+                            const float* __restrict__ scratch_c, const unsigned char* __restrict__ flags_c,
+                            int64_t num_chunks, float* __restrict__ scratch_s, unsigned char* __restrict__ flags_s,
+                            int64_t num_super) {
     const int lane = threadIdx.x & (LANES - 1);
     const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
     const int chunks = p.chunks;
-    const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch);
+    const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch_c);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
-    for (int64_t ck = group; ck < num_super; ck += num_groups) {
-        if (!(flags[ck] & kFlagOpenRight)) continue;   // only the super-chunk that holds the head of a crossing run
-        const uint32_t slot = keys[min((ck + 1) * kSuper, p.n) - 1];
-        VT acc[CPL], wr[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            int col = lane + c * LANES;
-            acc[c] = col < chunks ? Vec<VT>::ld(sv + (ck * 2 + 1) * chunks + col) : Vec<VT>::zero();
-            wr[c] = (col < chunks && OPT != kOptDense && slot != pad)
-                        ? Vec<VT>::ld(reinterpret_cast<const VT*>(up.cache) + (int64_t)slot * chunks + col)
-                        : Vec<VT>::zero();
-        }
-        // the run continues through every following super-chunk flagged Whole and ends in the first one that is
-        // not; partials are added in order (deterministic), kBatch loads in flight at a time
-        constexpr int kBatch = 8;
-        int64_t c2 = ck + 1;
-        bool more = c2 < num_super;
-        while (more) {
-            int take = 0;
-            while (take < kBatch && c2 + take < num_super) {
-                unsigned char f = flags[c2 + take];
-                ++take;
-                if (!(f & kFlagWhole)) { more = false; break; }
-            }
-            if (c2 + take >= num_super) more = false;
-            VT part[kBatch][CPL];
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) {
+    for (int64_t S = group; S < num_super; S += num_groups) {
+        const int64_t c0 = S * kSuperChunks;
+        const int64_t cend = min(c0 + (int64_t)kSuperChunks, num_chunks);
+        unsigned char sflag = 0;
+        for (int64_t g = c0; g < cend; ++g) {
+            const unsigned char f = flags_c[g];
+            if (g == c0 && (f & kFlagOpenLeft)) {         // the run that enters this super-chunk from the left
+                VT acc[CPL];
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     int col = lane + c * LANES;
-                    part[b][c] = (b < take && col < chunks) ? Vec<VT>::ld(sv + ((c2 + b) * 2) * chunks + col)
-                                                            : Vec<VT>::zero();
+                    acc[c] = col < chunks ? Vec<VT>::ld(sv + (c0 * 2) * chunks + col) : Vec<VT>::zero();
+                }
+                sflag |= kFlagOpenLeft;
+                if (f & kFlagWhole) {
+                    bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, c0 + 1, cend, chunks, lane, acc);
+                    if (!ended) sflag |= kFlagWhole;       // one run covers the whole super-chunk and goes on
+                }
+                store_partial<VT, LANES, CPL>(scratch_s, S, 0, chunks, lane, acc);
+            }
+            if (f & kFlagOpenRight) {                      // chunk g holds the head of a run that crosses its end
+                VT acc[CPL];
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    int col = lane + c * LANES;
+                    acc[c] = col < chunks ? Vec<VT>::ld(sv + (g * 2 + 1) * chunks + col) : Vec<VT>::zero();
+                }
+                bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, g + 1, cend, chunks, lane, acc);
+                if (ended) {
+                    const uint32_t slot = keys[min((g + 1) * (int64_t)kChunk, p.n) - 1];
+                    if (slot != pad) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
+                } else {                                   // continues into the next super-chunk
+                    store_partial<VT, LANES, CPL>(scratch_s, S, 1, chunks, lane, acc);
+                    sflag |= kFlagOpenRight;
                 }
             }
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) {
-                if (b < take) {
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[c], 1.f, part[b][c]);
-                }
-            }
-            c2 += take;
         }
-        if (slot != pad) apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc, wr);
+        if (lane == 0) flags_s[S] = sflag;
+    }
+}
+
+// Phase 2b: one group per run that started inside a super-chunk and crossed its end.
+template <typename VT, int LANES, int CPL, int OPT>
+__global__ void __launch_bounds__(kBwdThreads)
+bag_backward_phase2b_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
+                            const float* __restrict__ scratch_s, const unsigned char* __restrict__ flags_s,
+                            int64_t num_super) {
+    constexpr int64_t kSuper = (int64_t)kSuperChunks * kChunk;
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int chunks = p.chunks;
+    const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch_s);
+    const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
+    for (int64_t S = group; S < num_super; S += num_groups) {
+        if (!(flags_s[S] & kFlagOpenRight)) continue;
+        const uint32_t slot = keys[min((S + 1) * kSuper, p.n) - 1];
+        VT acc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int col = lane + c * LANES;
+            acc[c] = col < chunks ? Vec<VT>::ld(sv + (S * 2 + 1) * chunks + col) : Vec<VT>::zero();
+        }
+        chain_sum<VT, LANES, CPL>(sv, flags_s, S + 1, num_super, chunks, lane, acc);
+        if (slot != pad) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
     }
 }
 
@@ -405,25 +420,24 @@ bag_backward_weights_kernel(const BagParams p, const float* __restrict__ grad_ou
 }
 
 struct BwdLayout {
-    size_t sort, bag_of, wts, scratch, flags, total;
-    int64_t num_chunks;
+    size_t sort, bag_of, wts, scratch, flags, scratch_s, flags_s, total;
+    int64_t num_chunks, num_super;
 };
-// super-chunks for a group width: G = kBwdThreads / lanes chunks each; the layout is sized for the narrowest group
-// (lanes = 32 -> G = 8), which has the most super-chunks
-static inline int64_t num_super_for(int64_t num_chunks, int lanes) { return ceil_div(num_chunks, kBwdThreads / lanes); }
 
 BwdLayout bwd_layout(int64_t n, int dim) {
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     BwdLayout L;
     int64_t nn = n > 0 ? n : 1;
     L.num_chunks = ceil_div(nn, kChunk);
+    L.num_super = ceil_div(L.num_chunks, kSuperChunks);
     size_t off = 0;
     L.sort = off; off += align(radix_sort_workspace_bytes(nn));
     L.bag_of = off; off += align((size_t)nn * 4);
     L.wts = off; off += align((size_t)nn * 4);
-    const int64_t max_super = num_super_for(L.num_chunks, 32);
-    L.scratch = off; off += align((size_t)max_super * 2 * dim * 4);
-    L.flags = off; off += align((size_t)max_super);
+    L.scratch = off; off += align((size_t)L.num_chunks * 2 * dim * 4);
+    L.flags = off; off += align((size_t)L.num_chunks);
+    L.scratch_s = off; off += align((size_t)L.num_super * 2 * dim * 4);
+    L.flags_s = off; off += align((size_t)L.num_super);
     L.total = off;
     return L;
 }
@@ -453,6 +467,8 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     float* wts = reinterpret_cast<float*>(ws + L.wts);
     float* scratch = reinterpret_cast<float*>(ws + L.scratch);
     unsigned char* flags = reinterpret_cast<unsigned char*>(ws + L.flags);
+    float* scratch_s = reinterpret_cast<float*>(ws + L.scratch_s);
+    unsigned char* flags_s = reinterpret_cast<unsigned char*>(ws + L.flags_s);
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
 
     {
@@ -477,17 +493,15 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     up.dim = a->dim;
     // sorted positions in flight per group (tunable: CEBAG_BWD_UNROLL = 4 | 8; 8 only for one chunk per lane)
     static const int unroll_env = env_int("CEBAG_BWD_UNROLL", 4);
-    static const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 8);
+    static const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 32);
 #define LAUNCH_P1(VT, LANES, CPL, FAST, UNROLL)                                                                     \
     bag_backward_phase1_kernel<VT, LANES, CPL, OPT, FAST, UNROLL><<<grid, kBwdThreads, 0, stream>>>(                \
-        p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks, num_super)
+        p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks)
 #define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
     do {                                                                                                            \
-        const int64_t num_super = num_super_for(L.num_chunks, LANES);                                               \
         {                                                                                                           \
             KernelScope scope1(kKernBwdPhase1, stream);                                                             \
-            const int64_t cap = (int64_t)kNumSMs * bwd_ctas_per_sm;                                                 \
-            int grid = (int)(num_super < cap ? num_super : cap);                                                    \
+            int grid = grid_for(L.num_chunks * LANES, kBwdThreads, bwd_ctas_per_sm);                                \
             if (fast) {                                                                                             \
                 if (unroll_env >= 8 && CPL == 1) LAUNCH_P1(VT, LANES, CPL, true, 8);                                \
                 else LAUNCH_P1(VT, LANES, CPL, true, 4);                                                            \
@@ -496,10 +510,12 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
             }                                                                                                       \
         }                                                                                                           \
         {                                                                                                           \
-            KernelScope scope2(kKernBwdPhase2, stream);                                                             \
-            int grid = grid_for(num_super * LANES, kBwdThreads, 4);                                                 \
-            bag_backward_phase2_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(p, up, keys, scratch, \
-                                                                                              flags, num_super);    \
+            KernelScope scope2(kKernBwdPhase2, stream, 2);                                                          \
+            int grid = grid_for(L.num_super * LANES, kBwdThreads, 8);                                               \
+            bag_backward_phase2a_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(                     \
+                p, up, keys, scratch, flags, L.num_chunks, scratch_s, flags_s, L.num_super);                        \
+            bag_backward_phase2b_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(                     \
+                p, up, keys, scratch_s, flags_s, L.num_super);                                                      \
         }                                                                                                           \
     } while (0)
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);

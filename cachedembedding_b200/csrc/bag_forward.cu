@@ -1,10 +1,8 @@
 // Offsets-based segment-sum gather over the slot cache: the forward of F.embedding_bag on cuda_cached_weight
 // (reference call site recsys/models/dlrm.py:99-110).
 //
-// HBM-bound gather: per lookup 8 B slot id + 4D B row, per bag 4D B output (+ offsets).  One group of LANES
-// threads owns a bag; every lane moves 128-bit chunks.  To keep enough bytes in flight per SM with pooling
-// factor 1 (Criteo), each group works on kBagsPerIter consecutive bags at once: all offset loads, then all slot-id
-// loads, then all row loads are issued before any is consumed.
+// HBM/L2-bound gather: per lookup 8 B slot id + 4D B row, per bag 4D B output (+ offsets).  A group of LANES threads
+// (row width / 16 B) works on LANES consecutive bags per iteration; every lane moves 128-bit chunks.
 #include "bag_common.cuh"
 #include "profile.cuh"
 
@@ -14,79 +12,99 @@ namespace {
 
 constexpr int kFwdThreads = 256;
 
-template <typename VT, int LANES, int CPL, int kBagsPerIter>
+// lanes of this thread's group inside its warp (groups of one warp may be at different points of their loops)
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask() {
+    return LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane_id() & ~(LANES - 1)));
+}
+
+// A group of LANES threads takes LANES consecutive bags per iteration: lane l reads the offsets, the first slot id and
+// the first weight of bag g0 + l with coalesced loads (with pooling factor 1 that is all there is to read), then the
+// group walks the LANES bags, kUnroll at a time: slot ids are broadcast by shuffle, the kUnroll row loads are issued
+// back to back, and only bags longer than one entry enter the per-entry loop.  ~12 instructions per row instead of
+// >100 for the one-bag-per-group formulation (ncu: that one was issue-bound at 25 % occupancy).
+template <typename VT, int LANES, int CPL, int kUnroll>
 __global__ void __launch_bounds__(kFwdThreads)
 bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int lane = threadIdx.x & (LANES - 1);
+    const unsigned gmask = group_mask<LANES>();
     const int64_t group = ((int64_t)blockIdx.x * kFwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kFwdThreads / LANES;
     const VT* __restrict__ cache = reinterpret_cast<const VT*>(p.cache);
     VT* __restrict__ outv = reinterpret_cast<VT*>(out);
     const int chunks = p.chunks;
+    const bool mean = p.mode == CEBAG_MODE_MEAN;
 
-    for (int64_t g0 = group * kBagsPerIter; g0 < p.num_bags; g0 += num_groups * kBagsPerIter) {
-        int64_t lo[kBagsPerIter], hi[kBagsPerIter];
-        int64_t prev = load_offset(p, g0);
-        int64_t max_len = 0;
-#pragma unroll
-        for (int u = 0; u < kBagsPerIter; ++u) {
-            bool valid = g0 + u < p.num_bags;
-            int64_t next = valid ? load_offset(p, g0 + u + 1) : prev;
-            lo[u] = prev;
-            hi[u] = next;
-            prev = next;
-            max_len = max(max_len, hi[u] - lo[u]);
+    for (int64_t g0 = group * LANES; g0 < p.num_bags; g0 += num_groups * LANES) {
+        const int64_t g = g0 + lane;
+        const bool have = g < p.num_bags;
+        const int64_t my_lo = have ? load_offset(p, g) : 0;
+        const int64_t my_hi = have ? load_offset(p, g + 1) : 0;
+        const int my_len = (int)(my_hi - my_lo);
+        long long my_slot = -1;
+        float my_w = 1.f;
+        if (my_len > 0) {
+            my_slot = __ldg(p.slot_ids + my_lo);
+            if (p.psw) my_w = __ldg(p.psw + my_lo);
+            if (my_slot == p.padding_idx) my_slot = -1;
         }
-        VT acc[kBagsPerIter][CPL];
-        int32_t cnt[kBagsPerIter];
+        const int my_row_lo = (int)(bag_row(p, have ? g : 0) & 0xffffffffu);   // num_bags < 2^31
+        const int nb = (int)min((int64_t)LANES, p.num_bags - g0);
+
+#pragma unroll 1
+        for (int u0 = 0; u0 < nb; u0 += kUnroll) {
+            int sl[kUnroll], len[kUnroll];
+            float w[kUnroll];
+            VT acc[kUnroll][CPL];
 #pragma unroll
-        for (int u = 0; u < kBagsPerIter; ++u) {
-            cnt[u] = 0;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[u][c] = Vec<VT>::zero();
-        }
-        // round t takes the t-th entry of each of the kBagsPerIter bags: independent loads across bags
-        for (int64_t t = 0; t < max_len; ++t) {
-            int64_t s[kBagsPerIter];
-            float w[kBagsPerIter];
-#pragma unroll
-            for (int u = 0; u < kBagsPerIter; ++u) {
-                int64_t i = lo[u] + t;
-                bool live = i < hi[u];
-                s[u] = live ? __ldg(p.slot_ids + i) : -1;
-                w[u] = (live && p.psw) ? __ldg(p.psw + i) : 1.f;
-                if (s[u] == p.padding_idx) s[u] = -1;
+            for (int k = 0; k < kUnroll; ++k) {
+                const int src = min(u0 + k, LANES - 1);
+                sl[k] = (int)__shfl_sync(gmask, (int)my_slot, src, LANES);       // slot ids < 2^31
+                len[k] = __shfl_sync(gmask, my_len, src, LANES);
+                w[k] = __shfl_sync(gmask, my_w, src, LANES);
+                if (u0 + k >= nb) { sl[k] = -1; len[k] = 0; }
             }
-            VT v[kBagsPerIter][CPL];
 #pragma unroll
-            for (int u = 0; u < kBagsPerIter; ++u) {
+            for (int k = 0; k < kUnroll; ++k) {
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
-                    int col = lane + c * LANES;
-                    v[u][c] = (s[u] >= 0 && col < chunks) ? Vec<VT>::ld_stream(cache + s[u] * chunks + col)
-                                                          : Vec<VT>::zero();
+                    const int col = lane + c * LANES;
+                    acc[k][c] = (sl[k] >= 0 && col < chunks) ? Vec<VT>::ld_stream(cache + (int64_t)sl[k] * chunks + col)
+                                                             : Vec<VT>::zero();
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBagsPerIter; ++u) {
-                if (s[u] >= 0) {
-                    cnt[u] += 1;
+            for (int k = 0; k < kUnroll; ++k) {
+                if (u0 + k >= nb) continue;
+                int cnt = sl[k] >= 0 ? 1 : 0;
+                if (p.psw) {
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(acc[u][c], w[u], v[u][c]);
+                    for (int c = 0; c < CPL; ++c) acc[k][c] = Vec<VT>::scale(acc[k][c], w[k]);
                 }
-            }
-        }
+                if (len[k] > 1) {        // group-uniform: bags with more than one entry
+                    const int src = u0 + k;
+                    const int64_t lo = ((int64_t)__shfl_sync(gmask, (int)(my_lo >> 32), src, LANES) << 32) |
+                                       (unsigned)__shfl_sync(gmask, (int)(my_lo & 0xffffffff), src, LANES);
+                    for (int i = 1; i < len[k]; ++i) {
+                        long long s2 = __ldg(p.slot_ids + lo + i);
+                        if (s2 == p.padding_idx) continue;
+                        const float w2 = p.psw ? __ldg(p.psw + lo + i) : 1.f;
+                        ++cnt;
 #pragma unroll
-        for (int u = 0; u < kBagsPerIter; ++u) {
-            if (g0 + u < p.num_bags) {
-                float scale = (p.mode == CEBAG_MODE_MEAN && cnt[u] > 0) ? 1.f / (float)cnt[u] : 1.f;
-                int64_t row = bag_row(p, g0 + u);
+                        for (int c = 0; c < CPL; ++c) {
+                            const int col = lane + c * LANES;
+                            if (col < chunks) Vec<VT>::fma(acc[k][c], w2, Vec<VT>::ld_stream(cache + s2 * chunks + col));
+                        }
+                    }
+                }
+                const int row = __shfl_sync(gmask, my_row_lo, u0 + k, LANES);
+                const float scale = (mean && cnt > 0) ? 1.f / (float)cnt : 1.f;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
-                    int col = lane + c * LANES;
+                    const int col = lane + c * LANES;
                     if (col < chunks) {
-                        VT r = p.mode == CEBAG_MODE_MEAN ? Vec<VT>::scale(acc[u][c], scale) : acc[u][c];
-                        Vec<VT>::st_stream(outv + row * chunks + col, r);
+                        VT r = mean ? Vec<VT>::scale(acc[k][c], scale) : acc[k][c];
+                        Vec<VT>::st_stream(outv + (int64_t)row * chunks + col, r);
                     }
                 }
             }
@@ -99,7 +117,8 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
 int fill_bag_params(const cebag_bag_args* a, BagParams* p, const RowShape& rs) {
     CEBAG_REQUIRE(a != nullptr, "null args");
     CEBAG_REQUIRE(a->dim > 0 && a->cache_rows > 0, "cache shape");
-    CEBAG_REQUIRE(a->n >= 0 && a->num_bags >= 0, "sizes");
+    CEBAG_REQUIRE(a->n >= 0 && a->num_bags >= 0 && a->num_bags < ((int64_t)1 << 31), "sizes");
+    CEBAG_REQUIRE(a->cache_rows > 0 && (int64_t)a->cache_rows < ((int64_t)1 << 31), "cache_rows");
     CEBAG_REQUIRE(a->n == 0 || a->slot_ids != nullptr, "slot_ids");
     CEBAG_REQUIRE(a->num_bags == 0 || a->offsets != nullptr, "offsets");
     CEBAG_REQUIRE(a->mode == CEBAG_MODE_SUM || a->mode == CEBAG_MODE_MEAN, "mode");
@@ -142,26 +161,25 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     BagParams p;
     int rc = fill_bag_params(a, &p, rs);
     if (rc) return rc;
-    // bags in flight per group: 8 / CPL by default (tunable: CEBAG_FWD_BPI = 2 | 4 | 8)
-    static const int bpi_env = env_int("CEBAG_FWD_BPI", 0);
-    static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 8);
-#define LAUNCH_FWD_BPI(VT, LANES, CPL, BPI)                                                              \
+    // rows in flight per group (tunable: CEBAG_FWD_UNROLL = 4 | 8)
+    static const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
+    static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 16);
+#define LAUNCH_FWD_U(VT, LANES, CPL, UNROLL)                                                             \
     do {                                                                                                 \
-        int64_t groups = ceil_div(p.num_bags, BPI);                                                      \
+        int64_t groups = ceil_div(p.num_bags, LANES);                                                    \
         int grid = grid_for(groups * LANES, kFwdThreads, ctas_per_sm);                                   \
-        bag_forward_kernel<VT, LANES, CPL, BPI><<<grid, kFwdThreads, 0, stream>>>(p, out);               \
+        bag_forward_kernel<VT, LANES, CPL, UNROLL><<<grid, kFwdThreads, 0, stream>>>(p, out);            \
     } while (0)
 #define LAUNCH_FWD(VT, LANES, CPL)                                                                       \
     do {                                                                                                 \
-        int bpi = bpi_env ? bpi_env : (CPL == 1 ? 8 : CPL == 2 ? 4 : 2);                                 \
-        if (bpi >= 8 && CPL == 1) LAUNCH_FWD_BPI(VT, LANES, CPL, 8);                                     \
-        else if (bpi >= 4 && CPL <= 2) LAUNCH_FWD_BPI(VT, LANES, CPL, 4);                                \
-        else LAUNCH_FWD_BPI(VT, LANES, CPL, 2);                                                          \
+        if (unroll_env >= 8 && CPL == 1 && LANES >= 8) LAUNCH_FWD_U(VT, LANES, CPL, 8);                  \
+        else if (CPL <= 2) LAUNCH_FWD_U(VT, LANES, CPL, 4);                                              \
+        else LAUNCH_FWD_U(VT, LANES, CPL, 2);                                                            \
     } while (0)
     KernelScope scope(kKernForward, stream);
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_FWD);
 #undef LAUNCH_FWD
-#undef LAUNCH_FWD_BPI
+#undef LAUNCH_FWD_U
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }

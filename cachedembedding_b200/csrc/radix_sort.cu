@@ -14,7 +14,8 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 16;                               // keys per thread
 constexpr int kSortTile = kSortThreads * kSortItems;         // 4096 keys per CTA
-constexpr int kMaxBuckets = 256;
+constexpr int kMaxDigitBits = 11;                           // 21-bit slot ids sort in 2 passes
+constexpr int kMaxBuckets = 1 << kMaxDigitBits;
 
 template <bool FIRST>
 __device__ __forceinline__ uint32_t load_key(const void* keys_in, int64_t i) {
@@ -52,10 +53,10 @@ __global__ void __launch_bounds__(kSortThreads)
 sort_scatter_kernel(const void* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n, int shift,
                     int nbuckets, int num_tiles, const int32_t* __restrict__ hist_scanned,
                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-    __shared__ int32_t cnt[kSortWarps][kMaxBuckets];
+    __shared__ uint16_t cnt[kSortWarps][kMaxBuckets];   // per-warp bucket counts (<= 32 * kSortItems = 512)
     __shared__ int32_t gbase[kMaxBuckets];
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    for (int b = threadIdx.x; b < kSortWarps * kMaxBuckets; b += kSortThreads) (&cnt[0][0])[b] = 0;
+    for (int b = threadIdx.x; b < kSortWarps * nbuckets; b += kSortThreads) cnt[b / nbuckets][b % nbuckets] = 0;
     __syncthreads();
     const uint32_t mask = (uint32_t)nbuckets - 1u;
     const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortItems);
@@ -78,7 +79,7 @@ sort_scatter_kernel(const void* __restrict__ keys_in, const uint32_t* __restrict
         int32_t old = 0;
         if (valid && lane == leader) {
             old = cnt[warp][d];
-            cnt[warp][d] = old + __popc(peers);
+            cnt[warp][d] = (uint16_t)(old + __popc(peers));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[k] = old + __popc(peers & ((1u << lane) - 1u));
@@ -90,7 +91,7 @@ sort_scatter_kernel(const void* __restrict__ keys_in, const uint32_t* __restrict
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
             int32_t c = cnt[w][b];
-            cnt[w][b] = run;
+            cnt[w][b] = (uint16_t)run;
             run += c;
         }
         gbase[b] = hist_scanned[(int64_t)b * num_tiles + blockIdx.x];
@@ -145,7 +146,7 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
     uint32_t* vbuf[2] = {reinterpret_cast<uint32_t*>(ws + L.vals_a), reinterpret_cast<uint32_t*>(ws + L.vals_b)};
     int32_t* hist = reinterpret_cast<int32_t*>(ws + L.hist);
     int32_t* scan_ws = reinterpret_cast<int32_t*>(ws + L.scan_ws);
-    const int passes = (key_bits + 7) / 8;
+    const int passes = (key_bits + kMaxDigitBits - 1) / kMaxDigitBits;
     KernelScope scope(kKernSort, stream, 2 * passes);
     const int bits_per_pass = (key_bits + passes - 1) / passes;
     int shift = 0;
