@@ -237,7 +237,8 @@ def run_b200(args):
         last = first + count
         w_first, w_last = first // P, (last - 1) // P
         pf = ce.LookaheadPrefetcher(model) if overlap else None
-        handle = pf.submit(window_ids(w_first, host_inputs, batches)) if overlap else None
+        plan = dict(offsets=offsets, layout="sample_major" if world > 1 else "bag_major", layout_batch=B if world > 1 else 0)
+        handle = pf.submit(window_ids(w_first, host_inputs, batches), **plan) if overlap else None
         for w in range(w_first, w_last + 1):
             if overlap:
                 slots_window = torch.chunk(handle.wait(), P)
@@ -257,7 +258,7 @@ def run_b200(args):
             if overlap:
                 pf.window_enqueued()
                 if w < w_last:
-                    handle = pf.submit(window_ids(w + 1, host_inputs, batches))
+                    handle = pf.submit(window_ids(w + 1, host_inputs, batches), **plan)
         if overlap:
             pf.close()
         return h2d, d2h

@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
@@ -31,7 +31,7 @@ EXPORTS = (
     "cebag_host_device_pointer", "cebag_fill_uniform",
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_flush", "cebag_preload",
     "cebag_admit_row", "cebag_evict_slot",
-    "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused",
+    "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused", "cebag_bag_backward_plan",
     "cebag_bag_backward_coo", "cebag_bag_backward_dense", "cebag_bag_backward_weights",
 )
 
@@ -108,7 +108,8 @@ def _declare(lib):
     lib.cebag_backward_workspace_bytes.argtypes = [POINTER(BagArgs)]
     lib.cebag_backward_workspace_bytes.restype = c_size_t
     lib.cebag_bag_backward_fused.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_int32, c_float,
-                                             c_float, c_void_p, c_size_t, c_void_p]
+                                             c_float, c_void_p, c_size_t, c_int32, c_void_p]
+    lib.cebag_bag_backward_plan.argtypes = [POINTER(BagArgs), c_void_p, c_size_t, c_void_p]
     lib.cebag_bag_backward_coo.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]
     lib.cebag_bag_backward_dense.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cebag_bag_backward_weights.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]

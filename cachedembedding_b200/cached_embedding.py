@@ -84,12 +84,18 @@ class _CachedBagFunction(torch.autograd.Function):
             fused = owner._fused_optimizer if owner is not None else None
             if fused is not None:
                 nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
-                ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+                plan = owner._take_backward_plan(slot_ids, offsets, psw, mode, nbytes) \
+                    if hasattr(owner, "_take_backward_plan") else None
+                if plan is not None:
+                    ws = plan
+                    ws.record_stream(torch.cuda.current_stream())
+                else:
+                    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
                 state = owner.cache_weight_mgr.cuda_cached_state
                 _lib.check(lib.cebag_bag_backward_fused(
                     ctypes.byref(a), grad_out.data_ptr(), weight.data_ptr(),
                     state.data_ptr() if state is not None else None, fused["kind"], fused["lr"], fused["eps"],
-                    ws.data_ptr(), nbytes, stream))
+                    ws.data_ptr(), nbytes, 1 if plan is not None else 0, stream))
             elif owner is not None and not owner.sparse:
                 nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
                 ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
@@ -253,6 +259,43 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         if kinds[kind] == _lib.OPT_ROWWISE_ADAGRAD and self.cache_weight_mgr.cuda_cached_state is None:
             raise ValueError("row-wise Adagrad needs the per-row state: construct with fused_optimizer='rowwise_adagrad'")
         self._fused_optimizer = {"kind": kinds[kind], "lr": float(lr), "eps": float(eps)}
+
+    # ---- backward plans (look-ahead) ----------------------------------------------------------------------------------------
+    def plan_backward(self, slot_ids: torch.Tensor, offsets: torch.Tensor, layout="bag_major", layout_batch=0) -> bool:
+        """Run the gradient-independent half of the fused backward (lookup->bag map + radix sort by slot) for a batch NOW,
+        on the current stream, and keep it until the backward of a forward over the very same `slot_ids` tensor picks it
+        up.  A look-ahead driver calls this on its side stream right after prepare_ids.  Returns False (and does
+        nothing) when the fused backward is off or the bag is not in plain mode 'sum'."""
+        if self._fused_optimizer is None or self.mode != "sum" or slot_ids.dim() != 1:
+            return False
+        lib = _lib.load()
+        weight = self.cache_weight_mgr.cuda_cached_weight
+        offsets = offsets.to(weight.device)
+        if offsets.dtype not in (torch.int32, torch.int64):
+            offsets = offsets.long()
+        offsets = offsets.contiguous()
+        lay = _lib.LAYOUT_SAMPLE_MAJOR if layout == "sample_major" else _lib.LAYOUT_BAG_MAJOR
+        a = _bag_args(weight, slot_ids, offsets, None, self.include_last_offset, _lib.MODE_SUM, self.padding_idx, lay,
+                      int(layout_batch))
+        nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        _lib.check(lib.cebag_bag_backward_plan(ctypes.byref(a), ws.data_ptr(), nbytes, _stream_ptr()))
+        if not hasattr(self, "_bwd_plans"):
+            self._bwd_plans = {}
+        self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = (ws, offsets.data_ptr(), nbytes)
+        return True
+
+    def _take_backward_plan(self, slot_ids, offsets, psw, mode, nbytes):
+        plans = getattr(self, "_bwd_plans", None)
+        if not plans or psw is not None or mode != _lib.MODE_SUM:
+            return None
+        entry = plans.pop((slot_ids.data_ptr(), slot_ids.numel()), None)
+        if entry is None:
+            return None
+        ws, off_ptr, planned_bytes = entry
+        if planned_bytes != nbytes:
+            return None
+        return ws
 
     # ---- forward --------------------------------------------------------------------------------------------------------------
     def _embed(self, slot_ids, offsets, per_sample_weights, layout="bag_major", layout_batch=0):

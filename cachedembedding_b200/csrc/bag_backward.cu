@@ -448,9 +448,29 @@ int key_bits_for(int32_t cache_rows) {
     return bits;
 }
 
+// bag_of (+ per-lookup weights) and the radix sort: everything of the backward that does not need the gradient
+int plan_sorted_backward(const cebag_bag_args* a, const BagParams& p, const BwdLayout& L, char* ws, cudaStream_t stream) {
+    int32_t* bag_of = reinterpret_cast<int32_t*>(ws + L.bag_of);
+    float* wts = reinterpret_cast<float*>(ws + L.wts);
+    const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
+    {
+        KernelScope scope(kKernBagOf, stream, fast ? 1 : 2);
+        bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
+        CEBAG_LAUNCH_CHECK();
+        if (!fast) {
+            lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);
+            CEBAG_LAUNCH_CHECK();
+        }
+    }
+    const uint32_t *keys = nullptr, *vals = nullptr;
+    return radix_sort_slots(a->slot_ids, a->n, key_bits_for(a->cache_rows), ws + L.sort,
+                            radix_sort_workspace_bytes(a->n), fast ? reinterpret_cast<const uint32_t*>(bag_of) : nullptr,
+                            &keys, &vals, stream);
+}
+
 template <int OPT>
 int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* target, float* state, float lr,
-                        float eps, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        float eps, void* workspace, size_t workspace_bytes, bool has_plan, cudaStream_t stream) {
     if (a->n == 0) return CEBAG_OK;
     CEBAG_REQUIRE(grad_out != nullptr && target != nullptr, "grad_out / target");
     CEBAG_REQUIRE(workspace != nullptr, "workspace");
@@ -470,21 +490,13 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     float* scratch_s = reinterpret_cast<float*>(ws + L.scratch_s);
     unsigned char* flags_s = reinterpret_cast<unsigned char*>(ws + L.flags_s);
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
-
-    {
-        KernelScope scope(kKernBagOf, stream, fast ? 1 : 2);
-        bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
-        CEBAG_LAUNCH_CHECK();
-        if (!fast) {
-            lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);
-            CEBAG_LAUNCH_CHECK();
-        }
+    CEBAG_REQUIRE(!has_plan || fast, "a backward plan exists only for mode sum without per-sample weights");
+    if (!has_plan) {
+        rc = plan_sorted_backward(a, p, L, ws, stream);
+        if (rc) return rc;
     }
     const uint32_t *keys = nullptr, *vals = nullptr;
-    rc = radix_sort_slots(a->slot_ids, a->n, key_bits_for(a->cache_rows), ws + L.sort,
-                          radix_sort_workspace_bytes(a->n), fast ? reinterpret_cast<const uint32_t*>(bag_of) : nullptr,
-                          &keys, &vals, stream);
-    if (rc) return rc;
+    radix_sort_result(a->n, key_bits_for(a->cache_rows), ws + L.sort, &keys, &vals);
     UpdateParams up;
     up.cache = target;
     up.state = state;
@@ -535,17 +547,35 @@ extern "C" size_t cebag_backward_workspace_bytes(const cebag_bag_args* a) {
     return bwd_layout(a->n, a->dim).total;
 }
 
+extern "C" int cebag_bag_backward_plan(const cebag_bag_args* a, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(a != nullptr, "null args");
+    if (a->n == 0) return CEBAG_OK;
+    CEBAG_REQUIRE(a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr,
+                  "a backward plan exists only for mode sum without per-sample weights");
+    CEBAG_REQUIRE(workspace != nullptr && aligned16(workspace), "workspace");
+    CEBAG_REQUIRE(a->n < ((int64_t)1 << 31) && a->num_bags < ((int64_t)1 << 31), "backward size");
+    BwdLayout L = bwd_layout(a->n, a->dim);
+    CEBAG_REQUIRE(workspace_bytes >= L.total, "backward workspace too small");
+    RowShape rs = row_shape(a->dim, true);
+    BagParams p;
+    int rc = fill_bag_params(a, &p, rs);
+    if (rc) return rc;
+    return plan_sorted_backward(a, p, L, reinterpret_cast<char*>(workspace), stream);
+}
+
 extern "C" int cebag_bag_backward_fused(const cebag_bag_args* a, const float* grad_out, float* cache_rw,
                                         float* cache_state, int32_t optimizer, float lr, float eps, void* workspace,
-                                        size_t workspace_bytes, void* stream_) {
+                                        size_t workspace_bytes, int32_t workspace_has_plan, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CEBAG_REQUIRE(a != nullptr, "null args");
     if (optimizer == CEBAG_OPT_SGD)
-        return run_sorted_backward<kOptSgd>(a, grad_out, cache_rw, nullptr, lr, 0.f, workspace, workspace_bytes, stream);
+        return run_sorted_backward<kOptSgd>(a, grad_out, cache_rw, nullptr, lr, 0.f, workspace, workspace_bytes,
+                                            workspace_has_plan != 0, stream);
     if (optimizer == CEBAG_OPT_ROWWISE_ADAGRAD) {
         CEBAG_REQUIRE(cache_state != nullptr, "row-wise Adagrad needs cache_state");
         return run_sorted_backward<kOptAdagrad>(a, grad_out, cache_rw, cache_state, lr, eps, workspace,
-                                                workspace_bytes, stream);
+                                                workspace_bytes, workspace_has_plan != 0, stream);
     }
     set_error("unknown optimizer %d", optimizer);
     return CEBAG_ERR_INVALID;
@@ -557,7 +587,7 @@ extern "C" int cebag_bag_backward_dense(const cebag_bag_args* a, const float* gr
     CEBAG_REQUIRE(a != nullptr && grad_cache != nullptr, "null args");
     CEBAG_CUDA_CHECK(cudaMemsetAsync(grad_cache, 0, (size_t)a->cache_rows * a->dim * sizeof(float), stream));
     return run_sorted_backward<kOptDense>(a, grad_out, grad_cache, nullptr, 0.f, 0.f, workspace, workspace_bytes,
-                                          stream);
+                                          false, stream);
 }
 
 extern "C" int cebag_bag_backward_coo(const cebag_bag_args* a, const float* grad_out, float* values, void* stream_) {

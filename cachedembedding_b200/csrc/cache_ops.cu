@@ -394,22 +394,44 @@ fixup_kernel(const cebag_table t, const int64_t* __restrict__ ids, const int32_t
     }
 }
 
-// LFU counters += multiplicity.  A warp whose 32 ids share one slot (tiny tables, feature-major ids) adds 32 with one
-// atomic; otherwise every lane issues its own fire-and-forget reduction.
+// LFU counters += multiplicity.  Ids arrive feature-major, so a tile of consecutive ids hits few distinct slots for
+// small tables and mostly distinct ones for big tables: each CTA first aggregates its tile in a shared-memory hash
+// table (one shared atomic per id, one per warp when all 32 lanes agree), then issues one 64-bit global reduction per
+// distinct slot -- hot slots no longer serialise millions of global atomics.
+constexpr int kLfuTile = 2048;            // ids per CTA iteration
+constexpr int kLfuTable = 4096;           // hash entries (load factor <= 0.5)
+
 __global__ void __launch_bounds__(kThreads)
 lfu_count_kernel(const cebag_table t, const int64_t* __restrict__ slots, int64_t n) {
+    __shared__ int s_key[kLfuTable];
+    __shared__ int s_cnt[kLfuTable];
     const int lane = lane_id();
-    const int64_t span = ((n + 31) / 32) * 32;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < span; i += (int64_t)gridDim.x * kThreads) {
-        const bool live = i < n;
-        const long long s = live ? slots[i] : -1;
-        int same = 0;
-        __match_all_sync(0xffffffffu, s, &same);
-        if (same) {
-            if (live && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s), 32ull);
-        } else if (live) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s), 1ull);
+    for (int64_t base = (int64_t)blockIdx.x * kLfuTile; base < n; base += (int64_t)gridDim.x * kLfuTile) {
+        for (int e = threadIdx.x; e < kLfuTable; e += kThreads) { s_key[e] = -1; s_cnt[e] = 0; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kLfuTile / kThreads; ++k) {
+            const int64_t i = base + k * kThreads + threadIdx.x;
+            const bool live = i < n;
+            const int s = live ? (int)slots[i] : -1 - lane;
+            int same = 0;
+            __match_all_sync(0xffffffffu, s, &same);
+            int add = 1;
+            if (same) { add = 32; if (lane != 0) add = 0; }
+            if (live && add) {
+                unsigned h = ((unsigned)s * 2654435761u) >> 20;          // 12 bits
+                while (true) {
+                    int prev = atomicCAS(&s_key[h], -1, s);
+                    if (prev == -1 || prev == s) { atomicAdd(&s_cnt[h], add); break; }
+                    h = (h + 1) & (kLfuTable - 1);
+                }
+            }
         }
+        __syncthreads();
+        for (int e = threadIdx.x; e < kLfuTable; e += kThreads) {
+            if (s_cnt[e]) atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s_key[e]), (unsigned long long)s_cnt[e]);
+        }
+        __syncthreads();
     }
 }
 
@@ -638,7 +660,7 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
     }
     if (t->strategy == CEBAG_EVICT_LFU) {
         KernelScope scope(kKernLfuCount, stream);
-        lfu_count_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, stream>>>(*t, slot_ids_out, n);
+        lfu_count_kernel<<<grid_for(ceil_div(n, kLfuTile) * kThreads, kThreads, 8), kThreads, 0, stream>>>(*t, slot_ids_out, n);
         CEBAG_LAUNCH_CHECK();
     }
     return CEBAG_OK;

@@ -134,6 +134,16 @@ SortLayout sort_layout(int64_t n) {
 
 size_t radix_sort_workspace_bytes(int64_t n) { return sort_layout(n).total; }
 
+void radix_sort_result(int64_t n, int key_bits, void* workspace, const uint32_t** keys_sorted,
+                       const uint32_t** vals_sorted) {
+    SortLayout L = sort_layout(n);
+    char* ws = reinterpret_cast<char*>(workspace);
+    const int passes = (key_bits + kMaxDigitBits - 1) / kMaxDigitBits;
+    const bool in_b = ((passes - 1) & 1) != 0;
+    *keys_sorted = reinterpret_cast<const uint32_t*>(ws + (in_b ? L.keys_b : L.keys_a));
+    *vals_sorted = reinterpret_cast<const uint32_t*>(ws + (in_b ? L.vals_b : L.vals_a));
+}
+
 int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* workspace, size_t workspace_bytes,
                      const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
                      cudaStream_t stream) {

@@ -13,4 +13,8 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
                      const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
                      cudaStream_t stream);
 
+// Where radix_sort_slots leaves its result inside `workspace` (for callers that sort now and consume later).
+void radix_sort_result(int64_t n, int key_bits, void* workspace, const uint32_t** keys_sorted,
+                       const uint32_t** vals_sorted);
+
 }  // namespace cebag

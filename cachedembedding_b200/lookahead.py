@@ -52,6 +52,7 @@ class LookaheadPrefetcher:
     """
 
     def __init__(self, bag_or_mgr, priority: int = -1):
+        self.bag = bag_or_mgr if hasattr(bag_or_mgr, "cache_weight_mgr") else None
         self.mgr = getattr(bag_or_mgr, "cache_weight_mgr", bag_or_mgr)
         self.device = self.mgr.device
         self.stream = torch.cuda.Stream(device=self.device, priority=priority)
@@ -59,15 +60,20 @@ class LookaheadPrefetcher:
         self._saved_protect = self.mgr.protect_windows
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
 
-    def submit(self, ids) -> PrefetchHandle:
+    def submit(self, ids, ready: Optional[torch.cuda.Event] = None, offsets=None, layout="bag_major",
+               layout_batch=0) -> PrefetchHandle:
         """Enqueue prepare_ids(ids) on the side stream.  `ids` is a tensor or a list of tensors (the batches of the
         window, concatenated here like recsys/dlrm_main.py:259 does); they may live in (pinned) host memory, in which
-        case the H2D copies run on the side stream as well."""
+        case the H2D copies run on the side stream as well.  With `offsets` (one tensor for all batches, or one per
+        batch) the fused backward of every batch is planned on the side stream too (CachedEmbeddingBag.plan_backward).
+
+        Device ids must be complete when the side stream starts reading them.  Pass `ready` = an event recorded right
+        after they were produced; without it nothing is waited for (recording an event here would be too late: the
+        current stream already holds the whole window that this call is supposed to overlap)."""
         cur = torch.cuda.current_stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(cur)                          # ids produced on the current stream are complete
         side = self.stream
-        side.wait_event(ready)
+        if ready is not None:
+            side.wait_event(ready)
         if len(self._fences) == 2:
             side.wait_event(self._fences[0])       # window k-1 finished: its updates are in the rows we may evict
         with torch.cuda.stream(side):
@@ -75,6 +81,12 @@ class LookaheadPrefetcher:
             parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
             ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
             slot_ids = self.mgr.prepare_ids(ids_dev)
+            if offsets is not None and self.bag is not None and len(parts) >= 1:
+                # the gradient-independent half of every batch's fused backward also runs here, off the critical path;
+                # torch.chunk gives the same views the training loop will pass to forward
+                offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
+                for chunk, off in zip(torch.chunk(slot_ids, len(parts)), offs):
+                    self.bag.plan_backward(chunk, off, layout, layout_batch)
             done = torch.cuda.Event()
             done.record(side)
         for t in parts:

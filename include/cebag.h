@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 2
+#define CEBAG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -173,7 +173,14 @@ CEBAG_API size_t cebag_backward_workspace_bytes(const cebag_bag_args* a);
  * Deterministic: lookups are radix-sorted by slot and reduced in index order; no float atomics. */
 CEBAG_API int cebag_bag_backward_fused(const cebag_bag_args* a, const float* grad_out, float* cache_rw, float* cache_state,
                              int32_t optimizer, float lr, float eps, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             int32_t workspace_has_plan, void* stream);
+
+/* The integer half of the fused backward (lookup -> bag map, radix sort of the lookups by slot) for one batch, left in
+ * `workspace` (cebag_backward_workspace_bytes).  It depends only on slot_ids / offsets, not on the gradient, so a
+ * look-ahead driver runs it on its side stream right after prepare_ids; cebag_bag_backward_fused called with the same
+ * arguments, the same workspace and workspace_has_plan = 1 then starts at the segment-reduce kernels.
+ * Only for mode sum without per-sample weights (returns CEBAG_ERR_INVALID otherwise). */
+CEBAG_API int cebag_bag_backward_plan(const cebag_bag_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
 /* backward, compatibility forms for an external torch optimizer:
  *   coo:   values fp32[n, D] with values[i] = w_i * grad_out[bag(i)] (indices are slot_ids) -- the COO grad that

@@ -462,7 +462,7 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     grads = [[torch.randn(F * B, D, generator=gen) for _ in range(P)] for _ in range(8)]
     pf = ce.LookaheadPrefetcher(model)
     assert model.cache_weight_mgr.protect_windows == 2
-    h = pf.submit(torch.cat(windows[0]).pin_memory())          # host ids: the H2D copy rides the side stream too
+    h = pf.submit([w.pin_memory() for w in windows[0]], offsets=offsets.cuda())   # host ids: H2D rides the side stream
     for k in range(len(windows)):
         slots = h.wait()
         oslots = omodel.cache_weight_mgr.prepare_ids(torch.cat(windows[k]))
@@ -473,7 +473,7 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
             outs.append(out)
         pf.window_enqueued()
         if k + 1 < len(windows):
-            h = pf.submit(torch.cat(windows[k + 1]).cuda())
+            h = pf.submit([w.cuda() for w in windows[k + 1]], offsets=offsets.cuda())
         assert torch.equal(slots.cpu(), oslots), f"slot ids differ in window {k}"
         for s, g, out in zip(torch.chunk(oslots, P), grads[k], outs):
             oout = omodel(s, offsets)
@@ -487,6 +487,38 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     assert_maps_equal(model.cache_weight_mgr, omodel.cache_weight_mgr)
     model.cache_weight_mgr.flush(); omodel.cache_weight_mgr.flush()
     close(model.weight, omodel.weight)
+
+
+def test_planned_backward_is_bitwise_identical_to_inline():
+    """cebag_bag_backward_plan on a side stream + backward with workspace_has_plan gives the same bits as the inline path."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(12)
+    N, D, G = 3000, 128, 5000
+    weight = torch.randn(N, D, generator=gen)
+    res = []
+    for planned in (False, True):
+        model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), mode="sum", include_last_offset=True, sparse=True,
+                                      cache_ratio=1.0, warmup_ratio=1.0, evict_strategy=ce.EvictionStrategy.DATASET,
+                                      fused_optimizer="sgd", lr=0.3)
+        model.set_cache_op(False)
+        g2 = torch.Generator().manual_seed(5)
+        ids = torch.randint(0, N, (G,), generator=g2).cuda()
+        offsets = torch.arange(G + 1).cuda()
+        grad = torch.randn(G, D, generator=g2).cuda()
+        slots = model.cache_weight_mgr.prepare_ids(ids)
+        if planned:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                assert model.plan_backward(slots, offsets)
+            torch.cuda.current_stream().wait_stream(side)
+            assert len(model._bwd_plans) == 1
+        out = model(slots, offsets)
+        out.backward(grad)
+        if planned:
+            assert len(model._bwd_plans) == 0, "the plan was not consumed"
+        res.append(model.cache_weight_mgr.cuda_cached_weight.detach().cpu())
+    assert torch.equal(res[0], res[1])
 
 
 def test_two_window_protection_capacity_error():
