@@ -229,7 +229,7 @@ def run_b200(args):
         src = host_batches if host_inputs else batches
         return src[w * P:(w + 1) * P]
 
-    def run_steps(first, count, host_inputs, batches=None):
+    def run_steps(first, count, host_inputs, batches=None, overlap=overlap):
         """Steps [first, first+count).  host_inputs: ids start in pinned host memory and are copied H2D inside the
         region (every batch of a window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row is
         read back D2H per step.  With overlap the prepare_ids of window w+1 runs on a side stream under window w."""
@@ -237,7 +237,8 @@ def run_b200(args):
         last = first + count
         w_first, w_last = first // P, (last - 1) // P
         pf = ce.LookaheadPrefetcher(model) if overlap else None
-        plan = dict(offsets=offsets, layout="sample_major" if world > 1 else "bag_major", layout_batch=B if world > 1 else 0)
+        plan = dict(offsets=offsets, layout="sample_major" if world > 1 else "bag_major",
+                    layout_batch=B if world > 1 else 0) if not args.no_plan_side else {}
         handle = pf.submit(window_ids(w_first, host_inputs, batches), **plan) if overlap else None
         for w in range(w_first, w_last + 1):
             if overlap:
@@ -281,6 +282,11 @@ def run_b200(args):
 
     # ---- device-resident arm: warm-up, then exactly K timed steps -------------------------------------------------
     # warm-up is rounded to whole windows internally only for the *slot* bookkeeping: steps W..W+K-1 are timed.
+    # two untimed windows on scratch ids before anything is measured: first-touch costs of the caching allocator
+    # (cross-stream buffers of the look-ahead driver) and of the lazily created streams/events
+    scratch = [sample_ids(rows_dev, B, gen, dev) for _ in range(2 * P)]
+    run_steps(0, 2 * P, False, scratch)
+    del scratch
     # clocks are sampled from the warm-up to the end of the end-to-end arm: every arm runs the same steps, and the
     # K timed steps alone are shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local) if rank == 0 else None
@@ -295,8 +301,9 @@ def run_b200(args):
     miss_ratio_lookups = mgr._cache_miss / max(mgr._total_cache, 1)
 
     # ---- per-kernel timers on a replay of the same steps (CUDA events on the launching stream) ------------------
+    # (look-ahead off for this replay: every kernel is alone on the GPU, so its event-bracketed time is its own)
     _lib.profile_enable(True)
-    run_steps(W, K, False, arms["profile"])
+    run_steps(W, K, False, arms["profile"], overlap=False)
     torch.cuda.synchronize()
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
@@ -456,6 +463,7 @@ def main():
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="prepare_ids on the compute stream (reference order)")
+    ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:

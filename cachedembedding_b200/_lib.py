@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
@@ -56,7 +56,8 @@ class Table(Structure):
 
 
 class Workspace(Structure):
-    _fields_ = [("device", c_void_p), ("device_bytes", c_size_t), ("pinned", c_void_p)]
+    _fields_ = [("device", c_void_p), ("device_bytes", c_size_t), ("pinned", c_void_p),
+                ("copy_stream", c_void_p), ("copy_done_event", c_void_p)]
 
 
 class PrepareStats(Structure):

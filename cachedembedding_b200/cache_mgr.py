@@ -124,6 +124,8 @@ class CachedParamMgr(nn.Module):
             self.cuda_cached_state = None
         self._epoch = 0
         self.protect_windows = 1      # 2 while a LookaheadPrefetcher overlaps prepare_ids with the previous window
+        self._copy_stream = None      # set by the look-ahead driver: row copies of prepare_ids go to this stream
+        self._copy_done = None        # event recorded after them
         self._counters_pinned = torch.zeros(64, dtype=torch.int32).pin_memory()
 
         self.evict_backlist = torch.tensor([], device=dev)
@@ -165,7 +167,11 @@ class CachedParamMgr(nn.Module):
     def _workspace(self, t: _lib.Table, n_ids: int):
         nbytes = int(self._lib.cebag_prepare_workspace_bytes(ctypes.byref(t), n_ids))
         buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        ws = _lib.Workspace(buf.data_ptr(), nbytes, self._counters_pinned.data_ptr())
+        ws = _lib.Workspace(buf.data_ptr(), nbytes, self._counters_pinned.data_ptr(), None, None)
+        if self._copy_stream is not None and self._copy_done is not None:
+            ws.copy_stream = self._copy_stream.cuda_stream
+            ws.copy_done_event = self._copy_done.cuda_event
+            buf.record_stream(self._copy_stream)       # the copy kernels read their row lists from this buffer
         return ws, buf
 
     # ---- reference-compatible views of the maps (int64, like upstream's buffers) ------------------------------------

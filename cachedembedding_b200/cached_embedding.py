@@ -261,11 +261,13 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         self._fused_optimizer = {"kind": kinds[kind], "lr": float(lr), "eps": float(eps)}
 
     # ---- backward plans (look-ahead) ----------------------------------------------------------------------------------------
-    def plan_backward(self, slot_ids: torch.Tensor, offsets: torch.Tensor, layout="bag_major", layout_batch=0) -> bool:
+    def plan_backward(self, slot_ids: torch.Tensor, offsets: torch.Tensor, layout="bag_major", layout_batch=0,
+                      workspace_factory=None) -> bool:
         """Run the gradient-independent half of the fused backward (lookup->bag map + radix sort by slot) for a batch NOW,
         on the current stream, and keep it until the backward of a forward over the very same `slot_ids` tensor picks it
-        up.  A look-ahead driver calls this on its side stream right after prepare_ids.  Returns False (and does
-        nothing) when the fused backward is off or the bag is not in plain mode 'sum'."""
+        up.  A look-ahead driver calls this on its side stream right after prepare_ids (`workspace_factory(nbytes)` lets
+        it supply a recycled buffer).  Returns False (and does nothing) when the fused backward is off or the bag is not
+        in plain mode 'sum'."""
         if self._fused_optimizer is None or self.mode != "sum" or slot_ids.dim() != 1:
             return False
         lib = _lib.load()
@@ -278,7 +280,8 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         a = _bag_args(weight, slot_ids, offsets, None, self.include_last_offset, _lib.MODE_SUM, self.padding_idx, lay,
                       int(layout_batch))
         nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
-        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        ws = workspace_factory(nbytes) if workspace_factory is not None else \
+            torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
         _lib.check(lib.cebag_bag_backward_plan(ctypes.byref(a), ws.data_ptr(), nbytes, _stream_ptr()))
         if not hasattr(self, "_bwd_plans"):
             self._bwd_plans = {}

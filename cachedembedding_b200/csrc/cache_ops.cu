@@ -247,80 +247,51 @@ __device__ __forceinline__ void warp_copy_row(float* __restrict__ dst, const flo
     }
 }
 
-// swap: the j-th smallest missed row goes to the j-th lowest free slot; if that slot holds a victim it is written
-// back first.  One warp per row; both the victim row and the new row are loaded before either is stored, so the
-// host->device and device->host PCIe streams overlap.
-template <bool VEC>
+// Admission, step 1 (maps): the j-th smallest missed row goes to the j-th lowest free slot (A.4 steps 4-6).  Records
+// the row the slot held (the victim, or -1) for the copy kernels and updates both maps, the LFU counter, the window
+// stamp and the miss bitmap.  Everything after this kernel that only needs the maps (fix-up of the missed positions,
+// LFU counts, backward plans) can proceed while the rows are still moving.
 __global__ void __launch_bounds__(kThreads)
-swap_rows_kernel(const cebag_table t, const int32_t* __restrict__ miss_rows, const int32_t* __restrict__ free_slots,
-                 int64_t m) {
-    const int lane = lane_id();
-    const int64_t warp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const int64_t num_warps = ((int64_t)gridDim.x * kThreads) >> 5;
-    const int dim = t.dim;
-    constexpr int kMaxChunks = 4;  // register staging for rows up to 32 lanes * 4 chunks
-    for (int64_t j = warp; j < m; j += num_warps) {
+commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ miss_rows,
+                        const int32_t* __restrict__ free_slots, int32_t* __restrict__ victim_rows, int64_t m) {
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kThreads) {
         const int32_t row = miss_rows[j];
         const int32_t slot = free_slots[j];
         const int32_t old_row = t.slot2row[slot];
+        victim_rows[j] = old_row;
+        if (old_row >= 0) t.row2slot[old_row] = -1;
+        t.slot2row[slot] = row;
+        t.row2slot[row] = slot;
+        t.slot_epoch[slot] = t.epoch;
+        if (t.freq) t.freq[slot] = 0;
+        t.miss_bitmap[row >> 5] = 0u;   // every row of this word was missed in this call and is being admitted
+    }
+}
+
+// Admission, step 2 (rows), one warp per row with zero-copy 128-bit accesses to the pinned host table.
+// direction 1: victims HBM -> host table (write-back), direction 0: missed rows host table -> HBM (fill).
+// The two directions are separate launches: interleaving posted writes and reads from one kernel halves the PCIe
+// throughput of both (measured: 20-24 GB/s each way fused vs 51 GB/s for a pure gather; PCIe reads may not pass writes).
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+copy_rows_kernel(const cebag_table t, const int32_t* __restrict__ miss_rows, const int32_t* __restrict__ free_slots,
+                 const int32_t* __restrict__ victim_rows, int64_t m, int direction) {
+    const int lane = lane_id();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t num_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int dim = t.dim;
+    for (int64_t j = warp; j < m; j += num_warps) {
+        const int32_t slot = free_slots[j];
         float* crow = t.cache + (int64_t)slot * dim;
-        const float* hsrc = t.host_table + (int64_t)row * dim;
-        float* hdst = old_row >= 0 ? t.host_table + (int64_t)old_row * dim : nullptr;
-        const int width = VEC ? dim / 4 : dim;
-        if (width <= 32 * kMaxChunks) {
-            if (VEC) {
-                float4 vin[kMaxChunks], vout[kMaxChunks];
-#pragma unroll
-                for (int c = 0; c < kMaxChunks; ++c) {
-                    int col = lane + c * 32;
-                    if (col < width) {
-                        vin[c] = reinterpret_cast<const float4*>(hsrc)[col];
-                        if (hdst) vout[c] = reinterpret_cast<const float4*>(crow)[col];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < kMaxChunks; ++c) {
-                    int col = lane + c * 32;
-                    if (col < width) {
-                        if (hdst) reinterpret_cast<float4*>(hdst)[col] = vout[c];
-                        reinterpret_cast<float4*>(crow)[col] = vin[c];
-                    }
-                }
-            } else {
-                float vin[kMaxChunks], vout[kMaxChunks];
-#pragma unroll
-                for (int c = 0; c < kMaxChunks; ++c) {
-                    int col = lane + c * 32;
-                    if (col < width) {
-                        vin[c] = hsrc[col];
-                        if (hdst) vout[c] = crow[col];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < kMaxChunks; ++c) {
-                    int col = lane + c * 32;
-                    if (col < width) {
-                        if (hdst) hdst[col] = vout[c];
-                        crow[col] = vin[c];
-                    }
-                }
-            }
+        if (direction == 1) {
+            const int32_t old_row = victim_rows[j];
+            if (old_row < 0) continue;
+            warp_copy_row<VEC>(t.host_table + (int64_t)old_row * dim, crow, dim, lane);
+            if (lane == 0 && t.host_state && t.cache_state) t.host_state[old_row] = t.cache_state[slot];
         } else {
-            if (hdst) warp_copy_row<VEC>(hdst, crow, dim, lane);
-            __syncwarp();
-            warp_copy_row<VEC>(crow, hsrc, dim, lane);
-        }
-        if (lane == 0) {
-            if (old_row >= 0) {
-                t.row2slot[old_row] = -1;
-                if (t.host_state && t.cache_state) t.host_state[old_row] = t.cache_state[slot];
-            }
-            if (t.host_state && t.cache_state) t.cache_state[slot] = t.host_state[row];
-            t.slot2row[slot] = row;
-            t.row2slot[row] = slot;
-            t.slot_epoch[slot] = t.epoch;
-            if (t.freq) t.freq[slot] = 0;
-            t.miss_bitmap[row >> 5] = 0u;   // every row of this word was missed in this call and is being admitted
+            const int32_t row = miss_rows[j];
+            warp_copy_row<VEC>(crow, t.host_table + (int64_t)row * dim, dim, lane);
+            if (lane == 0 && t.host_state && t.cache_state) t.cache_state[slot] = t.host_state[row];
         }
     }
 }
@@ -436,7 +407,7 @@ lfu_count_kernel(const cebag_table t, const int64_t* __restrict__ slots, int64_t
 }
 
 struct PrepLayout {
-    size_t counters, select, miss_pos, miss_rows, free_slots, flags_a, flags_b, bitmap_sums, scan_ws, total;
+    size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, total;
     int64_t bitmap_blocks, words;
 };
 
@@ -453,6 +424,7 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     L.miss_pos = off; off += align((size_t)nn * 4);
     L.miss_rows = off; off += align((size_t)C * 4);
     L.free_slots = off; off += align((size_t)C * 4);
+    L.victim_rows = off; off += align((size_t)C * 4);
     L.flags_a = off; off += align((size_t)C * 4);
     L.flags_b = off; off += align((size_t)C * 4);
     L.bitmap_sums = off; off += align((size_t)(L.bitmap_blocks + 1) * 4);
@@ -535,6 +507,7 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
     int32_t* miss_pos = reinterpret_cast<int32_t*>(base + L.miss_pos);
     int32_t* miss_rows = reinterpret_cast<int32_t*>(base + L.miss_rows);
     int32_t* free_slots = reinterpret_cast<int32_t*>(base + L.free_slots);
+    int32_t* victim_rows = reinterpret_cast<int32_t*>(base + L.victim_rows);
     int32_t* flags_a = reinterpret_cast<int32_t*>(base + L.flags_a);
     int32_t* flags_b = reinterpret_cast<int32_t*>(base + L.flags_b);
     int32_t* bitmap_sums = reinterpret_cast<int32_t*>(base + L.bitmap_sums);
@@ -643,10 +616,41 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
             CEBAG_LAUNCH_CHECK();
         }
         {
-            KernelScope scope(kKernSwapRows, stream);
-            const int mgrid = grid_for(M * 32, kThreads, 8);
-            if (table_vec_ok(t)) swap_rows_kernel<true><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
-            else swap_rows_kernel<false><<<mgrid, kThreads, 0, stream>>>(*t, miss_rows, free_slots, M);
+            KernelScope scope(kKernFreeSlots, stream);
+            commit_admission_kernel<<<grid_for(M, kThreads, 8), kThreads, 0, stream>>>(*t, miss_rows, free_slots,
+                                                                                     victim_rows, M);
+        }
+        CEBAG_LAUNCH_CHECK();
+        {
+            // PCIe-bound: ~56 GB/s x ~2 us of latency is ~110 KB in flight, a few hundred rows.  A SMALL grid matters:
+            // under the look-ahead driver these kernels run next to the fwd/bwd kernels, and measured step time falls
+            // from 0.71 to 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 47 of
+            // 51 GB/s).  With a copy stream in the workspace the rows move there while `stream` goes on with the
+            // map-only work.
+            static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 48);
+            static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
+            cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
+            if (cstream != stream) {
+                cudaEvent_t committed;
+                CEBAG_CUDA_CHECK(cudaEventCreateWithFlags(&committed, cudaEventDisableTiming));
+                CEBAG_CUDA_CHECK(cudaEventRecord(committed, stream));
+                CEBAG_CUDA_CHECK(cudaStreamWaitEvent(cstream, committed, 0));
+                CEBAG_CUDA_CHECK(cudaEventDestroy(committed));   // released once the wait has been satisfied
+            }
+            const int64_t want = ceil_div(M * 32, swap_threads);
+            const int mgrid = (int)(want < swap_ctas ? want : swap_ctas);
+            const bool vec = table_vec_ok(t);
+            {
+                KernelScope scope(kKernSwapRows, cstream, E > 0 ? 2 : 1);
+                if (E > 0) {
+                    if (vec) copy_rows_kernel<true><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 1);
+                    else copy_rows_kernel<false><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 1);
+                }
+                if (vec) copy_rows_kernel<true><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 0);
+                else copy_rows_kernel<false><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 0);
+            }
+            if (cstream != stream && ws->copy_done_event)
+                CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->copy_done_event), cstream));
         }
         CEBAG_LAUNCH_CHECK();
         {

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 3
+#define CEBAG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -82,6 +82,10 @@ typedef struct cebag_workspace {
     void*  device;            /* device scratch                                                           */
     size_t device_bytes;
     void*  pinned;            /* >= 256 bytes of pinned host memory for counter read-back                 */
+    void*  copy_stream;       /* optional cudaStream_t: the PCIe row copies of prepare_ids are enqueued here (after the
+                                 maps are committed on `stream`) instead of on `stream`; the workspace must then stay
+                                 alive until copy_done_event has completed                                     */
+    void*  copy_done_event;   /* optional cudaEvent_t recorded on copy_stream after the row copies               */
 } cebag_workspace;
 
 /* What one prepare_ids call did (upstream: num_hits_history / num_miss_history / num_write_back_history,
