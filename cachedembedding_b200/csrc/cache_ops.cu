@@ -627,7 +627,7 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
             // from 0.71 to 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 47 of
             // 51 GB/s).  With a copy stream in the workspace the rows move there while `stream` goes on with the
             // map-only work.
-            static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 48);
+            static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
             static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
             cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
             if (cstream != stream) {

@@ -14,8 +14,9 @@ Hazards and how they are closed:
   * rows the in-flight window k still reads/updates must not be evicted by prepare(k+1): the manager protects the
     slots stamped by the last TWO windows (`protect_windows = 2`); the capacity rule becomes
     |rows(k) U rows(k+1)| <= cuda_row_num, checked before anything is changed;
-  * a victim may have been updated by window k-1's backward: the side stream waits for the event recorded after
-    window k-1's compute was enqueued (the copy stream is ordered after the side stream's map commit);
+  * a victim may have been updated by window k-1's backward: the stream that moves rows (the copy stream, ordered
+    after the side stream's map commit) waits for the event recorded after window k-1's compute was enqueued; the
+    map-only head of prepare_ids does not touch rows and is not held back;
   * slot ids (side stream) and rows (copy stream) are consumed on the compute stream: `PrefetchHandle.wait()` makes it
     wait for both completion events;
   * backward-plan buffers are a ring of two windows owned by this object: the buffers of window k-1 are reused for
@@ -93,13 +94,19 @@ class LookaheadPrefetcher:
         side = self.stream
         if ready is not None:
             side.wait_event(ready)
-        if len(self._fences) == 2:
-            side.wait_event(self._fences[0])       # window k-1 finished: its updates are in the rows we may evict
+        # window k-1 must have finished before its rows can be written back (its updates have to be in them) and
+        # before its plan buffers are recycled.  Only the ROW COPIES need that: with a copy stream the map-only head
+        # of prepare_ids (probe, victim selection, commit) starts at once and just the copy stream is fenced.
+        fence = self._fences[0] if len(self._fences) == 2 else None
         rows_done = None
         if self.copy_stream is not None:
+            if fence is not None:
+                self.copy_stream.wait_event(fence)
             rows_done = torch.cuda.Event()
             rows_done.record(self.copy_stream)     # instantiates the event; re-recorded after the row copies
             self.mgr._copy_stream, self.mgr._copy_done = self.copy_stream, rows_done
+        elif fence is not None:
+            side.wait_event(fence)
         parity = self._window & 1
         self._window += 1
         try:
@@ -111,6 +118,8 @@ class LookaheadPrefetcher:
                 if offsets is not None and self.bag is not None:
                     # the gradient-independent half of every batch's fused backward also runs here, off the critical
                     # path; torch.chunk gives the same views the training loop will pass to forward
+                    if fence is not None and self.copy_stream is not None:
+                        side.wait_event(fence)     # plan buffers of window k-1 are free again
                     offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
                     for j, (chunk, off) in enumerate(zip(torch.chunk(slot_ids, len(parts)), offs)):
                         self.bag.plan_backward(chunk, off, layout, layout_batch,
