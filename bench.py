@@ -397,6 +397,8 @@ def cpu_oracle_arm(workload, steps, warmup, budget_s=None):
     model = OracleCachedEmbeddingBag(N, D, sparse=True, mode="sum", include_last_offset=True,
                                      cache_ratio=wl["cache_ratio"], ids_freq_mapping=freq, warmup_ratio=0.7,
                                      evict_strategy=OStrategy.LFU,
+                                     # slots follow the UNSCALED table so that a window of full batches still fits
+                                     cuda_row_num=min(N, max(int(sum(wl["rows"]) * wl["cache_ratio"]), 1)),
                                      _weight=torch.empty(N, D).uniform_(-1.0 / N, 1.0 / N))
     opt = torch.optim.SGD(model.parameters(), lr=1.0)
     model.set_cache_op(False)
