@@ -193,10 +193,19 @@ def run_b200(args):
     for _ in range(args.freq_batches):
         ids = sample_ids(rows_dev, B, gen, dev)
         freq += torch.bincount(ids, minlength=N_loc)
-    model = ce.CachedEmbeddingBag(N_loc, D, sparse=True, mode="sum", include_last_offset=True,
-                                  cache_ratio=wl["cache_ratio"], ids_freq_mapping=freq, warmup_ratio=0.7,
-                                  evict_strategy=ce.EvictionStrategy.LFU, cuda_row_num=C_loc, init_seed=SEED,
-                                  fused_optimizer="sgd", lr=1.0)
+    common = dict(sparse=True, mode="sum", include_last_offset=True, cache_ratio=wl["cache_ratio"], warmup_ratio=0.7,
+                  evict_strategy=ce.EvictionStrategy.LFU, cuda_row_num=C_loc, init_seed=SEED, fused_optimizer="sgd",
+                  lr=1.0)
+    if world == 1:
+        model = ce.CachedEmbeddingBag(N_loc, D, ids_freq_mapping=freq, **common)
+    else:
+        # the reference's table-wise module (recsys/models/dlrm.py:53-68): every table with its rank and frequencies
+        table_freq = dict(zip(my_tables, torch.split(freq, rows_loc)))
+        cfgs = [ce.TablewiseEmbeddingBagConfig(rows_all[t], 0, assigned_rank=arrange[t],
+                                               ids_freq_mapping=table_freq.get(t, torch.zeros(1)))
+                for t in range(len(rows_all))]
+        model = ce.ParallelCachedEmbeddingBagTablewise(cfgs, D, **common)
+        model.enable_fused_exchange(not args.no_fused_exchange)
     del freq
     mgr = model.cache_weight_mgr
     model.set_cache_op(False)
@@ -216,13 +225,11 @@ def run_b200(args):
     else:
         grad_full = torch.randn(n_b, D, device=dev)
 
+    grad_holder = {"g": grad_full}
+
     def embed_step(slots):
-        if world > 1:
-            local_out = model._embed(slots, offsets, None, layout="sample_major", layout_batch=B)
-            out = dual_all_to_all_tablewise(local_out.view(B, F_loc * D), None, strides, dim_per_rank)
-        else:
-            out = model(slots, offsets)
-        out.backward(grad_full)
+        out = model(slots, offsets)          # table-wise: (B / W, F * D) after the exchange; single GPU: (F * B, D)
+        out.backward(grad_holder["g"])
         return out
 
     def window_ids(w, host_inputs, batches):
@@ -237,8 +244,7 @@ def run_b200(args):
         last = first + count
         w_first, w_last = first // P, (last - 1) // P
         pf = ce.LookaheadPrefetcher(model) if overlap else None
-        plan = dict(offsets=offsets, layout="sample_major" if world > 1 else "bag_major",
-                    layout_batch=B if world > 1 else 0) if not args.no_plan_side else {}
+        plan = dict(offsets=offsets) if not args.no_plan_side else {}
         handle = pf.submit(window_ids(w_first, host_inputs, batches), **plan) if overlap else None
         for w in range(w_first, w_last + 1):
             if overlap:
@@ -287,6 +293,11 @@ def run_b200(args):
     scratch = [sample_ids(rows_dev, B, gen, dev) for _ in range(2 * P)]
     run_steps(0, 2 * P, False, scratch)
     del scratch
+    if world > 1 and getattr(model, "_exchange", None) is not None:
+        # the "dense part" leaves its gradient where the fused backward reads it (no staging copy per step)
+        g = model._exchange.grad_tensor()
+        g.copy_(grad_full)
+        grad_holder["g"] = g
     # clocks are sampled from the warm-up to the end of the end-to-end arm: every arm runs the same steps, and the
     # K timed steps alone are shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local) if rank == 0 else None
@@ -352,7 +363,9 @@ def run_b200(args):
             "lookahead": "prepare_ids(window k+1) on a side stream under window k" if overlap else "serial (reference order)",
             "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
             "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
-            "parallelism": "single GPU" if world == 1 else f"table-wise x{world} + NCCL all-to-all of pooled embeddings",
+            "parallelism": "single GPU" if world == 1 else (
+                f"table-wise x{world}, pooled-embedding all-to-all " +
+                ("via NCCL" if args.no_fused_exchange else "fused into the fwd/bwd kernels over NVLink peer memory")),
             "l2": "inputs larger than L2: each step streams >= 2 x n_b x 512 B (1.7 GB at n_b = 1.7 M) vs 126 MB L2",
             "unique_rows_per_step": round(u_avg), "unique_hits": hit_u, "unique_misses": miss_u, "evicted_rows": evicted,
             "miss_ratio_lookups": round(miss_ratio_lookups, 5), "setup_s": round(setup_s, 1),
@@ -465,6 +478,7 @@ def main():
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="prepare_ids on the compute stream (reference order)")
+    ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: NCCL all-to-all instead of peer-memory kernels")
     ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     args = ap.parse_args()

@@ -12,6 +12,7 @@ from .cached_embedding import (CachedEmbeddingBag, FreqAwareEmbeddingBag, BaseEm
 from .parallel_cached_embedding import ParallelCachedEmbeddingBag
 from .parallel_cached_embedding_tablewise import ParallelCachedEmbeddingBagTablewise
 from .lookahead import LookaheadPrefetcher, PrefetchHandle
+from .fused_exchange import FusedExchange, PeerBuffer
 from .collectives import dual_all_to_all, dual_all_to_all_tablewise, get_partition
 
 __all__ = [

@@ -12,14 +12,15 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
 EVICT_LFU, EVICT_DATASET = 1, 2
 MODE_SUM, MODE_MEAN = 0, 1
 OPT_SGD, OPT_ROWWISE_ADAGRAD = 0, 1
-LAYOUT_BAG_MAJOR, LAYOUT_SAMPLE_MAJOR = 0, 1
+LAYOUT_BAG_MAJOR, LAYOUT_SAMPLE_MAJOR, LAYOUT_EXCHANGE = 0, 1, 2
+MAX_PEERS = 8
 FREQ_EMPTY = 2**63 - 1
 
 # every symbol include/cebag.h declares (tests check the library exports exactly these)
@@ -29,6 +30,7 @@ EXPORTS = (
     "cebag_profile_collect",
     "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
     "cebag_host_device_pointer", "cebag_fill_uniform",
+    "cebag_device_alloc", "cebag_device_free", "cebag_ipc_export", "cebag_ipc_import", "cebag_ipc_close",
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_flush", "cebag_preload",
     "cebag_admit_row", "cebag_evict_slot",
     "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused", "cebag_bag_backward_plan",
@@ -65,6 +67,11 @@ class PrepareStats(Structure):
                 ("miss_lookups", c_int64), ("total_lookups", c_int64)]
 
 
+class Exchange(Structure):
+    _fields_ = [("world", c_int32), ("feature_offset", c_int32), ("total_features", c_int32), ("reserved0", c_int32),
+                ("peer", c_void_p * 8)]
+
+
 class BagArgs(Structure):
     _fields_ = [
         ("cache", c_void_p), ("cache_rows", c_int32), ("dim", c_int32),
@@ -76,6 +83,7 @@ class BagArgs(Structure):
         ("padding_idx", c_int64),
         ("layout", c_int32),
         ("layout_batch", c_int64),
+        ("exchange", POINTER(Exchange)),
     ]
 
 
@@ -97,6 +105,11 @@ def _declare(lib):
     lib.cebag_host_unregister.argtypes = [c_void_p]
     lib.cebag_host_device_pointer.argtypes = [c_void_p, POINTER(c_void_p)]
     lib.cebag_fill_uniform.argtypes = [c_void_p, c_int64, c_float, c_float, c_uint64, c_void_p]
+    lib.cebag_device_alloc.argtypes = [POINTER(c_void_p), c_size_t]
+    lib.cebag_device_free.argtypes = [c_void_p]
+    lib.cebag_ipc_export.argtypes = [c_void_p, ctypes.c_char_p]
+    lib.cebag_ipc_import.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
+    lib.cebag_ipc_close.argtypes = [c_void_p]
     lib.cebag_prepare_workspace_bytes.argtypes = [POINTER(Table), c_int64]
     lib.cebag_prepare_workspace_bytes.restype = c_size_t
     lib.cebag_prepare_ids.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),

@@ -171,7 +171,6 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
     const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
     const int chunks = p.chunks;
-    const VT* __restrict__ gradv = reinterpret_cast<const VT*>(grad_out);
     const VT* __restrict__ cachev = reinterpret_cast<const VT*>(up.cache);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
 
@@ -195,14 +194,14 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
             const uint32_t my_val = mine ? vals[pos] : 0u;
             const int my_bag = VAL_IS_BAG ? (int)my_val : (mine ? bag_of[my_val] : 0);
             const float my_w = (VAL_IS_BAG || !mine) ? 1.f : wts[my_val];
-            const int my_grow = (int)bag_row(p, my_bag);
+            const float* my_gptr = bag_row_ptr(p, const_cast<float*>(grad_out), my_bag);
             const unsigned tailbits = __ballot_sync(gmask, mine && my_next != my_key) >> gshift;
             const int nl = (int)min((int64_t)LANES, end - sb);
 
 #pragma unroll 1
             for (int u0 = 0; u0 < nl; u0 += kUnroll) {
                 uint32_t k[kUnroll];
-                int grow[kUnroll];
+                const VT* grow[kUnroll];
                 float w[kUnroll];
                 bool live[kUnroll], tail[kUnroll];
 #pragma unroll
@@ -210,7 +209,7 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                     const int src = min(u0 + u, LANES - 1);
                     live[u] = u0 + u < nl;
                     k[u] = __shfl_sync(gmask, my_key, src, LANES);
-                    grow[u] = __shfl_sync(gmask, my_grow, src, LANES);
+                    grow[u] = reinterpret_cast<const VT*>(shfl_ptr(gmask, my_gptr, src, LANES));
                     w[u] = VAL_IS_BAG ? 1.f : __shfl_sync(gmask, my_w, src, LANES);
                     tail[u] = live[u] && ((tailbits >> (u0 + u)) & 1u);
                 }
@@ -221,7 +220,7 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                     for (int c = 0; c < CPL; ++c) {
                         const int col = lane + c * LANES;
                         const bool ok = live[u] && col < chunks;
-                        gr[u][c] = ok ? Vec<VT>::ld_stream(gradv + (int64_t)grow[u] * chunks + col) : Vec<VT>::zero();
+                        gr[u][c] = ok ? Vec<VT>::ld_stream(grow[u] + col) : Vec<VT>::zero();
                         // current row, needed where a run ends inside this chunk
                         const bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
                         wr[u][c] = need_row ? Vec<VT>::ld(cachev + (int64_t)k[u] * chunks + col) : Vec<VT>::zero();
@@ -472,7 +471,7 @@ template <int OPT>
 int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* target, float* state, float lr,
                         float eps, void* workspace, size_t workspace_bytes, bool has_plan, cudaStream_t stream) {
     if (a->n == 0) return CEBAG_OK;
-    CEBAG_REQUIRE(grad_out != nullptr && target != nullptr, "grad_out / target");
+    CEBAG_REQUIRE((grad_out != nullptr || a->layout == CEBAG_LAYOUT_EXCHANGE) && target != nullptr, "grad_out / target");
     CEBAG_REQUIRE(workspace != nullptr, "workspace");
     CEBAG_REQUIRE(a->n < ((int64_t)1 << 31) && a->num_bags < ((int64_t)1 << 31), "backward size");
     BwdLayout L = bwd_layout(a->n, a->dim);

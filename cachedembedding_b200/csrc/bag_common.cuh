@@ -25,6 +25,13 @@ struct BagParams {
     int32_t include_last;
     int32_t mode;
     int32_t layout;
+    // CEBAG_LAYOUT_EXCHANGE: rows of out / grad_out live in the peer buffers (fp32[B_j, F, D] on rank j)
+    int32_t exch_world;
+    int32_t exch_feature_offset;
+    int32_t exch_total_features;
+    int32_t exch_base;            // B / world
+    int32_t exch_rem;             // B % world: the first exch_rem ranks own exch_base + 1 samples
+    float*  exch_peer[CEBAG_MAX_PEERS];
 };
 
 __device__ __forceinline__ int64_t load_offset(const BagParams& p, int64_t g) {
@@ -41,6 +48,30 @@ __device__ __forceinline__ int64_t bag_row(const BagParams& p, int64_t g) {
         return b * p.layout_features + f;
     }
     return g;
+}
+
+// address of the out / grad_out row of bag g; `local` is the caller's own out / grad_out buffer
+__device__ __forceinline__ float* bag_row_ptr(const BagParams& p, float* local, int64_t g) {
+    if (p.layout == CEBAG_LAYOUT_EXCHANGE) {
+        const int64_t f = g / p.layout_batch, b = g - f * p.layout_batch;
+        const int64_t big = (int64_t)p.exch_rem * (p.exch_base + 1);      // samples held by the ranks with one extra
+        int j;
+        int64_t b_local;
+        if (b < big) { j = (int)(b / (p.exch_base + 1)); b_local = b - (int64_t)j * (p.exch_base + 1); }
+        else { j = p.exch_rem + (int)((b - big) / p.exch_base); b_local = b - big - (int64_t)(j - p.exch_rem) * p.exch_base; }
+        float* base = p.exch_peer[0];
+#pragma unroll
+        for (int q = 1; q < CEBAG_MAX_PEERS; ++q) base = (j == q) ? p.exch_peer[q] : base;
+        return base + (b_local * p.exch_total_features + p.exch_feature_offset + f) * p.dim;
+    }
+    return local + bag_row(p, g) * p.dim;
+}
+
+__device__ __forceinline__ const float* shfl_ptr(unsigned mask, const float* ptr, int src, int width) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(ptr);
+    unsigned lo = __shfl_sync(mask, (unsigned)(v & 0xffffffffu), src, width);
+    unsigned hi = __shfl_sync(mask, (unsigned)(v >> 32), src, width);
+    return reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
 }
 
 template <typename VT> struct Vec;

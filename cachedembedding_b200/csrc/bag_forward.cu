@@ -31,7 +31,6 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int64_t group = ((int64_t)blockIdx.x * kFwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kFwdThreads / LANES;
     const VT* __restrict__ cache = reinterpret_cast<const VT*>(p.cache);
-    VT* __restrict__ outv = reinterpret_cast<VT*>(out);
     const int chunks = p.chunks;
     const bool mean = p.mode == CEBAG_MODE_MEAN;
 
@@ -48,7 +47,7 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
             if (p.psw) my_w = __ldg(p.psw + my_lo);
             if (my_slot == p.padding_idx) my_slot = -1;
         }
-        const int my_row_lo = (int)(bag_row(p, have ? g : 0) & 0xffffffffu);   // num_bags < 2^31
+        const float* my_out = bag_row_ptr(p, out, have ? g : 0);
         const int nb = (int)min((int64_t)LANES, p.num_bags - g0);
 
 #pragma unroll 1
@@ -97,14 +96,14 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
                         }
                     }
                 }
-                const int row = __shfl_sync(gmask, my_row_lo, u0 + k, LANES);
+                VT* orow = reinterpret_cast<VT*>(const_cast<float*>(shfl_ptr(gmask, my_out, u0 + k, LANES)));
                 const float scale = (mean && cnt > 0) ? 1.f / (float)cnt : 1.f;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     const int col = lane + c * LANES;
                     if (col < chunks) {
                         VT r = mean ? Vec<VT>::scale(acc[k][c], scale) : acc[k][c];
-                        Vec<VT>::st_stream(outv + (int64_t)row * chunks + col, r);
+                        Vec<VT>::st_stream(orow + col, r);
                     }
                 }
             }
@@ -138,10 +137,29 @@ int fill_bag_params(const cebag_bag_args* a, BagParams* p, const RowShape& rs) {
     p->layout = a->layout;
     p->layout_batch = 1;
     p->layout_features = 1;
+    p->exch_world = 0;
     if (a->layout == CEBAG_LAYOUT_SAMPLE_MAJOR) {
         CEBAG_REQUIRE(a->layout_batch > 0 && a->num_bags % a->layout_batch == 0, "sample-major layout needs G = F * B");
         p->layout_batch = a->layout_batch;
         p->layout_features = a->num_bags / a->layout_batch;
+    } else if (a->layout == CEBAG_LAYOUT_EXCHANGE) {
+        const cebag_exchange* x = a->exchange;
+        CEBAG_REQUIRE(x != nullptr, "exchange layout needs a cebag_exchange");
+        CEBAG_REQUIRE(x->world >= 1 && x->world <= CEBAG_MAX_PEERS, "exchange world");
+        CEBAG_REQUIRE(a->layout_batch >= x->world && a->num_bags % a->layout_batch == 0, "exchange layout needs G = F_local * B");
+        p->layout_batch = a->layout_batch;
+        p->layout_features = a->num_bags / a->layout_batch;
+        CEBAG_REQUIRE(x->feature_offset >= 0 && x->feature_offset + p->layout_features <= x->total_features,
+                      "exchange feature range");
+        p->exch_world = x->world;
+        p->exch_feature_offset = x->feature_offset;
+        p->exch_total_features = x->total_features;
+        p->exch_base = (int32_t)(a->layout_batch / x->world);
+        p->exch_rem = (int32_t)(a->layout_batch % x->world);
+        for (int q = 0; q < CEBAG_MAX_PEERS; ++q) {
+            p->exch_peer[q] = q < x->world ? x->peer[q] : nullptr;
+            CEBAG_REQUIRE(q >= x->world || (x->peer[q] != nullptr && aligned16(x->peer[q])), "exchange peer pointer");
+        }
     } else {
         CEBAG_REQUIRE(a->layout == CEBAG_LAYOUT_BAG_MAJOR, "layout");
     }
@@ -156,7 +174,7 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CEBAG_REQUIRE(a != nullptr, "null args");
     if (a->num_bags == 0) return CEBAG_OK;
-    CEBAG_REQUIRE(out != nullptr, "out");
+    CEBAG_REQUIRE(out != nullptr || a->layout == CEBAG_LAYOUT_EXCHANGE, "out");
     RowShape rs = row_shape(a->dim, aligned16(a->cache) && aligned16(out));
     BagParams p;
     int rc = fill_bag_params(a, &p, rs);

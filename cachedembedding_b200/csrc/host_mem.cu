@@ -84,6 +84,39 @@ extern "C" int cebag_host_device_pointer(void* host_ptr, void** out_dev_ptr) {
     return CEBAG_OK;
 }
 
+extern "C" int cebag_device_alloc(void** out_ptr, size_t bytes) {
+    CEBAG_REQUIRE(out_ptr != nullptr && bytes > 0, "device_alloc arguments");
+    CEBAG_CUDA_CHECK(cudaMalloc(out_ptr, bytes));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_device_free(void* ptr) {
+    if (ptr) CEBAG_CUDA_CHECK(cudaFree(ptr));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_ipc_export(void* ptr, unsigned char handle[64]) {
+    CEBAG_REQUIRE(ptr != nullptr && handle != nullptr, "ipc_export arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CEBAG_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_ipc_import(const unsigned char handle[64], void** out_ptr) {
+    CEBAG_REQUIRE(handle != nullptr && out_ptr != nullptr, "ipc_import arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CEBAG_CUDA_CHECK(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_ipc_close(void* ptr) {
+    if (ptr) CEBAG_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return CEBAG_OK;
+}
+
 extern "C" int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi, uint64_t seed, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     CEBAG_REQUIRE(dst != nullptr && count >= 0, "fill_uniform arguments");

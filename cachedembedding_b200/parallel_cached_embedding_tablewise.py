@@ -98,6 +98,11 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
             with torch.no_grad():
                 indices = self.cache_weight_mgr.prepare_ids(indices)
         # (B, F_loc, D) written by the kernel == torch.cat(out.split(B), 1) of the bag-major result
+        if self._use_fused_exchange(batch_size, per_sample_weights):
+            output_full = self._forward_fused(indices, offsets, batch_size)
+            if shape_hook is not None:
+                output_full = shape_hook(output_full)
+            return output_full
         local_out = self._embed(indices, offsets, per_sample_weights, layout="sample_major", layout_batch=batch_size)
         local_out = local_out.view(batch_size, n_local * self.embedding_dim)
         scatter_strides = split_sizes(batch_size, self.world_size)
@@ -106,6 +111,36 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         if shape_hook is not None:
             output_full = shape_hook(output_full)
         return output_full
+
+    # ---- fused exchange over NVLink peer memory (fused_exchange.py) ----------------------------------------------------
+    def enable_fused_exchange(self, flag: bool = True):
+        """Fold the pooled-embedding all-to-all (and its backward) into the gather / optimizer kernels.  Needs the fused
+        optimizer (`set_fused_optimizer`), mode 'sum', no per-sample weights and more than one rank."""
+        self._fused_exchange_on = bool(flag)
+        if not flag and getattr(self, "_exchange", None) is not None:
+            self._exchange.close()
+            self._exchange = None
+
+    def _use_fused_exchange(self, batch_size, per_sample_weights) -> bool:
+        return (getattr(self, "_fused_exchange_on", False) and self.world_size > 1 and per_sample_weights is None
+                and self.mode == "sum" and self._fused_optimizer is not None and batch_size >= self.world_size)
+
+    def _forward_fused(self, slot_ids, offsets, batch_size):
+        from .fused_exchange import FusedExchange, _FusedTablewiseFunction
+        exch = getattr(self, "_exchange", None)
+        if exch is None or exch.B != batch_size:
+            if exch is not None:
+                exch.close()
+            total_features = len(self.rank_of_tables)
+            feature_offset = sum(1 for r in self.rank_of_tables if r < self.rank)
+            exch = FusedExchange(batch_size, total_features, feature_offset, self.embedding_dim, self.process_group)
+            self._exchange = exch
+        offsets = offsets.to(slot_ids.device)
+        if offsets.dtype not in (torch.int32, torch.int64):
+            offsets = offsets.long()
+        out = _FusedTablewiseFunction.apply(self.cache_weight_mgr.cuda_cached_weight, slot_ids.contiguous().view(-1),
+                                            offsets.contiguous(), self, exch)
+        return out
 
     def split_along_rank(self, batch_size, indices: torch.Tensor, offsets: torch.Tensor = None,
                          per_sample_weights=None):

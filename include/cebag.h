@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 4
+#define CEBAG_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -39,9 +39,13 @@ typedef enum cebag_status {
 enum { CEBAG_EVICT_LFU = 1, CEBAG_EVICT_DATASET = 2 };        /* EvictionStrategy (recsys/models/dlrm.py:66,80) */
 enum { CEBAG_MODE_SUM = 0, CEBAG_MODE_MEAN = 1 };              /* F.embedding_bag mode                           */
 enum { CEBAG_OPT_SGD = 0, CEBAG_OPT_ROWWISE_ADAGRAD = 1 };
+#define CEBAG_MAX_PEERS 8
 enum { CEBAG_LAYOUT_BAG_MAJOR = 0,     /* out[g, :]                       -- what F.embedding_bag returns            */
-       CEBAG_LAYOUT_SAMPLE_MAJOR = 1   /* out[(g % B) * F + g / B, :]     -- the (B, F, D) view the DLRM shape hooks
-                                          build (recsys/models/dlrm.py:26-30), written directly by the kernel   */ };
+       CEBAG_LAYOUT_SAMPLE_MAJOR = 1,  /* out[(g % B) * F + g / B, :]     -- the (B, F, D) view the DLRM shape hooks
+                                          build (recsys/models/dlrm.py:26-30), written directly by the kernel   */
+       CEBAG_LAYOUT_EXCHANGE = 2       /* table-wise sharding with the all-to-all FUSED into the kernel: bag (f, b) of
+                                          this rank's f-th table lives in the buffer of the rank that owns sample b
+                                          (cebag_exchange), reached over NVLink peer memory                     */ };
 
 #define CEBAG_FREQ_EMPTY INT64_MAX     /* LFU counter of an empty slot (upstream: sys.maxsize)                   */
 
@@ -119,6 +123,13 @@ CEBAG_API int cebag_host_register(void* ptr, size_t bytes);                   /*
 CEBAG_API int cebag_host_unregister(void* ptr);
 CEBAG_API int cebag_host_device_pointer(void* host_ptr, void** out_dev_ptr);  /* device-visible alias of a pinned ptr    */
 
+/* Device memory that other processes of the node can map (plain cudaMalloc + CUDA IPC), for cebag_exchange.peer. */
+CEBAG_API int cebag_device_alloc(void** out_ptr, size_t bytes);
+CEBAG_API int cebag_device_free(void* ptr);
+CEBAG_API int cebag_ipc_export(void* ptr, unsigned char handle[64]);
+CEBAG_API int cebag_ipc_import(const unsigned char handle[64], void** out_ptr);
+CEBAG_API int cebag_ipc_close(void* ptr);
+
 /* Fill fp32[count] (device or pinned host memory) with U(lo, hi) from a counter-based generator; the value of
  * element i depends only on (seed, i).  Replaces _weight_alloc's uniform_(-1/N, 1/N) (A.2) for tables that are
  * too large to initialise from one host thread. */
@@ -147,6 +158,21 @@ CEBAG_API int cebag_preload(cebag_table* t, const int32_t* rows, const int64_t* 
 CEBAG_API int cebag_admit_row(cebag_table* t, int64_t row, int64_t slot, void* stream);
 CEBAG_API int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream);
 
+/* Peer buffers of the fused pooled-embedding exchange (replaces dual_all_to_all_tablewise, A.6 / SURVEY K15).
+ * Rank j owns samples [start_j, start_j + B_j) of the global batch B (torch.tensor_split rule: the first B % world
+ * ranks hold one more) and a buffer fp32[B_j, total_features, D] with features in rank-major order; peer[j] is that
+ * buffer mapped into THIS process (CUDA IPC over NVLink; peer[own rank] is the local buffer).  The forward stores
+ * every pooled row of this rank's tables straight into the owner's buffer; the backward loads every gradient row
+ * straight from it.  The caller orders the kernels of different ranks (a barrier after the forward's stores and
+ * before the backward's loads). */
+typedef struct cebag_exchange {
+    int32_t world;                   /* ranks, <= CEBAG_MAX_PEERS                                              */
+    int32_t feature_offset;          /* position of this rank's first table in the rank-major feature order    */
+    int32_t total_features;          /* F over all ranks                                                       */
+    int32_t reserved0;
+    float*  peer[CEBAG_MAX_PEERS];
+} cebag_exchange;
+
 /* ---- embedding bag over the slot cache (F.embedding_bag on cuda_cached_weight, A.2) --------------------------- */
 typedef struct cebag_bag_args {
     const float*   cache;          /* fp32[C, D]                                                            */
@@ -162,7 +188,9 @@ typedef struct cebag_bag_args {
     int32_t        mode;           /* CEBAG_MODE_*                                                          */
     int64_t        padding_idx;    /* slot id to skip, or -1                                                */
     int32_t        layout;         /* CEBAG_LAYOUT_* of out / grad_out                                      */
-    int64_t        layout_batch;   /* B for CEBAG_LAYOUT_SAMPLE_MAJOR (num_bags == F * B)                   */
+    int64_t        layout_batch;   /* B for CEBAG_LAYOUT_SAMPLE_MAJOR / _EXCHANGE (num_bags == F_local * B)  */
+    const cebag_exchange* exchange;/* CEBAG_LAYOUT_EXCHANGE only: where out (forward) / grad_out (backward) live;
+                                      the out / grad_out pointer arguments are then ignored                  */
 } cebag_bag_args;
 
 /* forward: out fp32[G, D] (or sample-major).  Replaces F.embedding_bag (recsys/models/dlrm.py:99-110). */

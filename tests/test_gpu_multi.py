@@ -104,7 +104,66 @@ def _columnwise_worker(rank, world, port, results):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_tablewise_worker, _columnwise_worker])
+def _fused_exchange_worker(rank, world, port, results):
+    """Fused peer-memory exchange == NCCL all-to-all path, bit for bit on the pooled output, and within 1e-5 on the
+    tables after several steps with evictions."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import cachedembedding_b200 as ce
+    gen = torch.Generator().manual_seed(3)
+    rows = [500, 40, 3000, 7, 1200]
+    ranks = [0, 1, 1, 0, 1]
+    D, B = 128, 37                                   # B not divisible by the world
+    weights = [torch.randn(n, D, generator=gen) * 0.1 for n in rows]
+    mine = [t for t, r in enumerate(ranks) if r == rank]
+    bags = []
+    for fused in (False, True):
+        cfgs = [ce.TablewiseEmbeddingBagConfig(n, 0, assigned_rank=r, initial_weight=w.clone())
+                for n, r, w in zip(rows, ranks, weights)]
+        bag = ce.ParallelCachedEmbeddingBagTablewise(cfgs, embedding_dim=D, include_last_offset=True, mode="sum",
+                                                     cache_ratio=0.2, warmup_ratio=0.5, sparse=True,
+                                                     evict_strategy=ce.EvictionStrategy.LFU,
+                                                     fused_optimizer="sgd", lr=0.25)
+        bag.enable_fused_exchange(fused)
+        bags.append(bag)
+    strides = [B // world + int(i < B % world) for i in range(world)]
+    ok = True
+    for step in range(4):
+        # the local KJT: my tables only, ids already re-based to the local concatenated table (A.6)
+        local_off, parts, lens_all = 0, [], []
+        for t in mine:
+            lens = torch.randint(0, 4, (B,), generator=gen)
+            ids = (torch.rand(int(lens.sum()), generator=gen) ** 2 * rows[t]).long().clamp_(0, rows[t] - 1) + local_off
+            parts.append(ids); lens_all.append(lens); local_off += rows[t]
+        # every rank draws from the same generator stream: advance it for the other rank's tables too
+        for t in range(len(rows)):
+            if t not in mine:
+                lens = torch.randint(0, 4, (B,), generator=gen)
+                torch.rand(int(lens.sum()), generator=gen)
+        values = torch.cat(parts).cuda()
+        offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.cat(lens_all), 0)]).cuda()
+        grad = torch.randn(B, len(rows) * D, generator=gen)
+        my_grad = grad.split(strides, 0)[rank].cuda()
+        outs = []
+        for bag in bags:
+            out = bag(values, offsets)
+            outs.append(out.detach().clone())
+            out.backward(my_grad)
+        ok = ok and torch.equal(outs[0], outs[1])
+    for bag in bags:
+        bag.cache_weight_mgr.flush()
+    ok = ok and torch.allclose(bags[0].weight, bags[1].weight, rtol=1e-5, atol=1e-6)
+    ok = ok and sum(bags[1].num_write_back_history) > 0
+    ok = ok and not torch.equal(bags[1].weight, torch.cat([weights[t] for t in mine]))   # it did train
+    results[rank] = bool(ok)
+    dist.barrier()
+    bags[1].enable_fused_exchange(False)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_tablewise_worker, _columnwise_worker, _fused_exchange_worker])
 def test_parallel_bags_two_ranks(worker):
     _need_two_gpus()
     world = 2
