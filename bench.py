@@ -54,17 +54,18 @@ WORKLOADS = {
 }
 
 
-def rank_arrange(rows, world):
-    if world in REF_RANK_ARRANGE_1TB and len(rows) == 26:
+def rank_arrange(rows, world, placement="auto"):
+    """table -> rank.  The reference's hard-coded maps where it has them (Criteo-1TB, world 2 and 4,
+    /root/reference/recsys/utils/misc.py:198-206); otherwise (it has none for world 8) a snake over the tables sorted by
+    rows: every rank gets ceil(F / world) or floor(F / world) tables -- lookups per step are equal per table, so this
+    balances kernel time -- and one of the `world` largest tables each, which balances host memory and cache demand."""
+    if placement == "auto" and world in REF_RANK_ARRANGE_1TB and len(rows) == 26:
         return REF_RANK_ARRANGE_1TB[world]
-    # greedy: biggest table to the rank with the fewest rows so far, ties to the rank with fewer tables
-    load = [[0, 0, r] for r in range(world)]
+    order = sorted(range(len(rows)), key=lambda i: -rows[i])
     arrange = [0] * len(rows)
-    for t in sorted(range(len(rows)), key=lambda i: -rows[i]):
-        load.sort(key=lambda x: (x[0], x[1]))
-        arrange[t] = load[0][2]
-        load[0][0] += rows[t]
-        load[0][1] += 1
+    for pos, t in enumerate(order):
+        lap, k = divmod(pos, world)
+        arrange[t] = k if lap % 2 == 0 else world - 1 - k
     return arrange
 
 
@@ -164,7 +165,7 @@ def run_b200(args):
     rows_all = list(wl["rows"])
     D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
     # every rank's tables must fit the host: scale rows down only if they do not
-    arrange = rank_arrange(rows_all, world)
+    arrange = rank_arrange(rows_all, world, args.placement)
     need_gb = sum(rows_all) * D * 4 / 1e9
     avail_gb = host_mem_available_gb()
     row_scale = args.row_scale
@@ -177,8 +178,13 @@ def run_b200(args):
     rows_loc = [rows_all[t] for t in my_tables]
     F, F_loc = len(rows_all), len(my_tables)
     N_loc = sum(rows_loc)
-    # slots follow the UNSCALED table (a window of the full batch must still fit when rows are scaled down)
-    C_loc = min(N_loc, max(int(sum(wl["rows"][t] for t in my_tables) * wl["cache_ratio"]), 1))
+    # HBM slot budget = cache_ratio of the UNSCALED table (a window of full batches must still fit when rows are scaled
+    # down).  With table-wise sharding the budget is split evenly over the ranks: the reference sizes each rank's
+    # cache as cache_ratio x its local rows, which leaves a rank that holds only small tables with fewer slots than
+    # one look-ahead window of a 65536 batch touches (its own capacity assert fires); demand per rank is set by the
+    # number of tables, not by their rows.
+    total_slots = max(int(sum(wl["rows"]) * wl["cache_ratio"]), 1)
+    C_loc = min(N_loc, total_slots // world)
     K, W = args.steps, args.warmup
     total_steps = W + K
     windows = (total_steps + P - 1) // P
@@ -226,6 +232,8 @@ def run_b200(args):
         grad_full = torch.randn(n_b, D, device=dev)
 
     grad_holder = {"g": grad_full}
+    # one look-ahead driver for the whole run: its streams and plan buffers are warmed once
+    prefetcher = {"pf": ce.LookaheadPrefetcher(model) if overlap else None}
 
     def embed_step(slots):
         out = model(slots, offsets)          # table-wise: (B / W, F * D) after the exchange; single GPU: (F * B, D)
@@ -243,7 +251,10 @@ def run_b200(args):
         h2d = d2h = 0
         last = first + count
         w_first, w_last = first // P, (last - 1) // P
-        pf = ce.LookaheadPrefetcher(model) if overlap else None
+        pf = prefetcher["pf"] if overlap else None
+        saved_protect = mgr.protect_windows
+        if not overlap:
+            mgr.protect_windows = 1          # reference order: only the current window is protected
         plan = dict(offsets=offsets) if not args.no_plan_side else {}
         handle = pf.submit(window_ids(w_first, host_inputs, batches), **plan) if overlap else None
         for w in range(w_first, w_last + 1):
@@ -267,7 +278,8 @@ def run_b200(args):
                 if w < w_last:
                     handle = pf.submit(window_ids(w + 1, host_inputs, batches), **plan)
         if overlap:
-            pf.close()
+            pf.drain()
+        mgr.protect_windows = saved_protect
         return h2d, d2h
 
     def timed(first, count, host_inputs, batches=None):
@@ -326,6 +338,8 @@ def run_b200(args):
     e2e_ms, h2d, d2h = timed(W, K, True)
     clocks = sampler.stop() if sampler else None
 
+    if prefetcher["pf"] is not None:
+        prefetcher["pf"].close()
     lookups_per_step = B * F                                  # whole job, all ranks
     value = lookups_per_step * K / (ms_total / 1e3)
     e2e_value = lookups_per_step * K / (e2e_ms / 1e3)
@@ -361,6 +375,7 @@ def run_b200(args):
             "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
                         f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
             "lookahead": "prepare_ids(window k+1) on a side stream under window k" if overlap else "serial (reference order)",
+            "tables_per_rank": [sum(1 for a in arrange if a == q) for q in range(world)],
             "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
             "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
             "parallelism": "single GPU" if world == 1 else (
@@ -478,6 +493,8 @@ def main():
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="prepare_ids on the compute stream (reference order)")
+    ap.add_argument("--placement", default="auto", choices=["auto", "snake"],
+                    help="auto: the reference's table->rank map where it has one, else the snake; snake: always")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: NCCL all-to-all instead of peer-memory kernels")
     ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)

@@ -139,6 +139,13 @@ class LookaheadPrefetcher:
         ev.record(torch.cuda.current_stream(self.device))
         self._fences.append(ev)
 
+    def drain(self):
+        """Wait for everything submitted so far; the driver stays usable (streams, plan buffers and protection kept)."""
+        self.stream.synchronize()
+        if self.copy_stream is not None:
+            self.copy_stream.synchronize()
+        self._fences.clear()
+
     def close(self):
         """Back to the reference's one-window protection (waits for the side and copy streams)."""
         self.stream.synchronize()
