@@ -279,8 +279,18 @@ bag_backward_phase2a_kernel(const BagParams p, const UpdateParams up, const uint
         const int64_t c0 = S * kSuperChunks;
         const int64_t cend = min(c0 + (int64_t)kSuperChunks, num_chunks);
         unsigned char sflag = 0;
+        // the 16 chunk flags of this super-chunk in one 128-bit load (the flag array is padded to a multiple of 16)
+        static_assert(kSuperChunks == 16, "one uint4 of flags per super-chunk");
+        const uint4 fw = *reinterpret_cast<const uint4*>(flags_c + c0);
+        const unsigned fwords[4] = {fw.x, fw.y, fw.z, fw.w};
+        if ((fw.x | fw.y | fw.z | fw.w) == 0u) {          // no run crosses a chunk boundary here
+            if (lane == 0) flags_s[S] = 0;
+            continue;
+        }
         for (int64_t g = c0; g < cend; ++g) {
-            const unsigned char f = flags_c[g];
+            const int gi = (int)(g - c0);
+            const unsigned char f = (unsigned char)((fwords[gi >> 2] >> ((gi & 3) * 8)) & 0xffu);
+            if (f == 0) continue;
             if (g == c0 && (f & kFlagOpenLeft)) {         // the run that enters this super-chunk from the left
                 VT acc[CPL];
 #pragma unroll
@@ -434,7 +444,7 @@ BwdLayout bwd_layout(int64_t n, int dim) {
     L.bag_of = off; off += align((size_t)nn * 4);
     L.wts = off; off += align((size_t)nn * 4);
     L.scratch = off; off += align((size_t)L.num_chunks * 2 * dim * 4);
-    L.flags = off; off += align((size_t)L.num_chunks);
+    L.flags = off; off += align((size_t)L.num_super * kSuperChunks);
     L.scratch_s = off; off += align((size_t)L.num_super * 2 * dim * 4);
     L.flags_s = off; off += align((size_t)L.num_super);
     L.total = off;

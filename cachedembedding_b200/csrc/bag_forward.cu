@@ -23,7 +23,9 @@ __device__ __forceinline__ unsigned group_mask() {
 // group walks the LANES bags, kUnroll at a time: slot ids are broadcast by shuffle, the kUnroll row loads are issued
 // back to back, and only bags longer than one entry enter the per-entry loop.  ~12 instructions per row instead of
 // >100 for the one-bag-per-group formulation (ncu: that one was issue-bound at 25 % occupancy).
-template <typename VT, int LANES, int CPL, int kUnroll>
+// FAST: mode sum, no per-sample weights, no padding index, bag-major output -- the reference's DLRM call; the weight,
+// count, padding and output-pointer bookkeeping compiles away.
+template <typename VT, int LANES, int CPL, int kUnroll, bool FAST>
 __global__ void __launch_bounds__(kFwdThreads)
 bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int lane = threadIdx.x & (LANES - 1);
@@ -32,7 +34,9 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int64_t num_groups = (int64_t)gridDim.x * kFwdThreads / LANES;
     const VT* __restrict__ cache = reinterpret_cast<const VT*>(p.cache);
     const int chunks = p.chunks;
-    const bool mean = p.mode == CEBAG_MODE_MEAN;
+    const bool mean = !FAST && p.mode == CEBAG_MODE_MEAN;
+    const float* __restrict__ psw = FAST ? nullptr : p.psw;
+    const long long padding = FAST ? -1 : (long long)p.padding_idx;
 
     for (int64_t g0 = group * LANES; g0 < p.num_bags; g0 += num_groups * LANES) {
         const int64_t g = g0 + lane;
@@ -44,10 +48,10 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
         float my_w = 1.f;
         if (my_len > 0) {
             my_slot = __ldg(p.slot_ids + my_lo);
-            if (p.psw) my_w = __ldg(p.psw + my_lo);
-            if (my_slot == p.padding_idx) my_slot = -1;
+            if (psw) my_w = __ldg(psw + my_lo);
+            if (my_slot == padding) my_slot = -1;
         }
-        const float* my_out = bag_row_ptr(p, out, have ? g : 0);
+        const float* my_out = FAST ? nullptr : bag_row_ptr(p, out, have ? g : 0);
         const int nb = (int)min((int64_t)LANES, p.num_bags - g0);
 
 #pragma unroll 1
@@ -60,7 +64,7 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
                 const int src = min(u0 + k, LANES - 1);
                 sl[k] = (int)__shfl_sync(gmask, (int)my_slot, src, LANES);       // slot ids < 2^31
                 len[k] = __shfl_sync(gmask, my_len, src, LANES);
-                w[k] = __shfl_sync(gmask, my_w, src, LANES);
+                w[k] = FAST ? 1.f : __shfl_sync(gmask, my_w, src, LANES);
                 if (u0 + k >= nb) { sl[k] = -1; len[k] = 0; }
             }
 #pragma unroll
@@ -76,7 +80,7 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
             for (int k = 0; k < kUnroll; ++k) {
                 if (u0 + k >= nb) continue;
                 int cnt = sl[k] >= 0 ? 1 : 0;
-                if (p.psw) {
+                if (psw) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) acc[k][c] = Vec<VT>::scale(acc[k][c], w[k]);
                 }
@@ -86,8 +90,8 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
                                        (unsigned)__shfl_sync(gmask, (int)(my_lo & 0xffffffff), src, LANES);
                     for (int i = 1; i < len[k]; ++i) {
                         long long s2 = __ldg(p.slot_ids + lo + i);
-                        if (s2 == p.padding_idx) continue;
-                        const float w2 = p.psw ? __ldg(p.psw + lo + i) : 1.f;
+                        if (s2 == padding) continue;
+                        const float w2 = psw ? __ldg(psw + lo + i) : 1.f;
                         ++cnt;
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) {
@@ -96,7 +100,8 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
                         }
                     }
                 }
-                VT* orow = reinterpret_cast<VT*>(const_cast<float*>(shfl_ptr(gmask, my_out, u0 + k, LANES)));
+                VT* orow = FAST ? reinterpret_cast<VT*>(out) + (g0 + u0 + k) * chunks
+                                : reinterpret_cast<VT*>(const_cast<float*>(shfl_ptr(gmask, my_out, u0 + k, LANES)));
                 const float scale = (mean && cnt > 0) ? 1.f / (float)cnt : 1.f;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
@@ -182,11 +187,14 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     // rows in flight per group (tunable: CEBAG_FWD_UNROLL = 4 | 8)
     static const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
     static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 16);
+    const bool fast_path = a->per_sample_weights == nullptr && a->mode == CEBAG_MODE_SUM && a->padding_idx < 0 &&
+                           a->layout == CEBAG_LAYOUT_BAG_MAJOR;
 #define LAUNCH_FWD_U(VT, LANES, CPL, UNROLL)                                                             \
     do {                                                                                                 \
         int64_t groups = ceil_div(p.num_bags, LANES);                                                    \
         int grid = grid_for(groups * LANES, kFwdThreads, ctas_per_sm);                                   \
-        bag_forward_kernel<VT, LANES, CPL, UNROLL><<<grid, kFwdThreads, 0, stream>>>(p, out);            \
+        if (fast_path) bag_forward_kernel<VT, LANES, CPL, UNROLL, true><<<grid, kFwdThreads, 0, stream>>>(p, out);   \
+        else bag_forward_kernel<VT, LANES, CPL, UNROLL, false><<<grid, kFwdThreads, 0, stream>>>(p, out);            \
     } while (0)
 #define LAUNCH_FWD(VT, LANES, CPL)                                                                       \
     do {                                                                                                 \

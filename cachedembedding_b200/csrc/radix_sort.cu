@@ -38,9 +38,11 @@ sort_hist_kernel(const void* __restrict__ keys_in, int64_t n, int shift, int nbu
         int64_t i = base + (int64_t)k * kSortThreads + threadIdx.x;
         bool valid = i < n;
         uint32_t d = valid ? ((load_key<FIRST>(keys_in, i) >> shift) & mask) : (0x80000000u | (uint32_t)lane_id());
-        // warp-aggregate equal digits before touching shared memory (skewed slots are the common case)
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (valid && (__ffs(peers) - 1) == lane_id()) atomicAdd(&h[d], __popc(peers));
+        // a warp whose 32 keys share the digit (hot slots of small tables) adds once; otherwise plain shared atomics
+        int same = 0;
+        __match_all_sync(0xffffffffu, d, &same);
+        if (same) { if (lane_id() == 0 && valid) atomicAdd(&h[d], 32); }
+        else if (valid) atomicAdd(&h[d], 1);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nbuckets; b += kSortThreads) hist[(int64_t)b * num_tiles + blockIdx.x] = h[b];
