@@ -363,9 +363,20 @@ def run_b200(args):
             kernels[name]["achieved_gbs"] = alg[name] / (ms / cnt / 1e3) / 1e9
     dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_step"])
     achieved = kernels[dom]["achieved_gbs"]
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same launch shape
+    # (profiles/r1b_fwd_bwd_sort.summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); only for that shape
+    ncu_traffic = {"bag_forward": 911.0e6, "bag_backward_phase1": 968.0e6} if (
+        args.workload == "criteo1tb" and world == 1) else {}
+    traffic = ncu_traffic.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg[dom])}
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg[dom]),
+                "note": ("algorithmic bytes count every looked-up row (n x 4D); a batch has only ~%d unique rows, which "
+                         "stay in the 126 MB L2, so DRAM sees mostly the output write: a fraction above 1 is L2 reuse, "
+                         "not skipped work" % round(u_avg))}
+    if traffic:
+        roofline["dram_gbs"] = round(traffic / (kernels[dom]["ms_per_step"] * K / kernels[dom]["launch_groups"] / 1e3) / 1e9, 1)
+        roofline["dram_frac"] = round(roofline["dram_gbs"] / peak, 4)
 
     line = {
         "metric": "embedding lookups/sec (fwd+bwd)", "value": value, "unit": "lookups/s", "n_gpus": world,

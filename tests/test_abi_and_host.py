@@ -152,3 +152,23 @@ def test_all_to_all_exchange_world2_gloo():
     results = mgr.dict()
     mp.spawn(_exchange_worker, args=(world, port, results), nprocs=world, join=True)
     assert all(results[r] for r in range(world)), dict(results)
+
+
+def test_reference_import_lines_resolve_after_install():
+    """The reference's own import statements (recsys/models/dlrm.py:15-16, recsys/utils/misc.py:8,
+    benchmark/benchmark_cache.py:16, benchmark/benchmark_fbgemm_uvm.py:3) work against this package."""
+    import subprocess
+    import sys
+    code = (
+        "from cachedembedding_b200 import colossalai_compat; colossalai_compat.install()\n"
+        "from colossalai.nn.parallel.layers import ParallelCachedEmbeddingBag, EvictionStrategy, "
+        "TablewiseEmbeddingBagConfig, ParallelCachedEmbeddingBagTablewise\n"
+        "from colossalai.nn.parallel.layers import CachedEmbeddingBag, EvictionStrategy\n"
+        "from colossalai.nn.parallel.layers.cache_embedding import CachedEmbeddingBag as C2\n"
+        "import cachedembedding_b200 as ce\n"
+        "assert CachedEmbeddingBag is ce.CachedEmbeddingBag is C2 and EvictionStrategy.LFU.value == 1\n"
+        "cfg = TablewiseEmbeddingBagConfig(num_embeddings=10, cuda_row_num=4, assigned_rank=0, ids_freq_mapping=None)\n"
+        "assert cfg.buffer_size == 50_000\n"
+        "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
