@@ -51,6 +51,9 @@ WORKLOADS = {
     "criteo1tb": dict(rows=CRITEO_1TB_ROWS, dim=128, batch=65536, prefetch=8, cache_ratio=0.01),
     "kaggle": dict(rows=CRITEO_KAGGLE_ROWS, dim=128, batch=4096, prefetch=8, cache_ratio=0.01),
     "plumbing": dict(rows=[100000] * 26, dim=16, batch=512, prefetch=1, cache_ratio=0.05),
+    # BASELINE.json configs[4]: one 1e9-row table (512 GB at dim 128 -- rows are scaled to the host's RAM, see
+    # config.row_scale); choose the slot fraction with --cache-ratio (0.001 / 0.01 / 0.1)
+    "zipf1e9": dict(rows=[1_000_000_000], dim=128, batch=65536 * 26, prefetch=8, cache_ratio=0.01),
 }
 
 
@@ -162,6 +165,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     wl = dict(WORKLOADS[args.workload])
+    if args.cache_ratio > 0:
+        wl["cache_ratio"] = args.cache_ratio
     rows_all = list(wl["rows"])
     D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
     # every rank's tables must fit the host: scale rows down only if they do not
@@ -500,6 +505,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="criteo1tb", choices=sorted(WORKLOADS))
+    ap.add_argument("--cache-ratio", type=float, default=0.0, help="override the workload's cache_ratio")
     ap.add_argument("--row-scale", type=int, default=0, help="divide table rows by this (0 = only if the host lacks RAM)")
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")

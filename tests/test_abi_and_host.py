@@ -172,3 +172,16 @@ def test_reference_import_lines_resolve_after_install():
         "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_limit_buff_index_copyer_chunks():
+    from cachedembedding_b200 import LimitBuffIndexCopyer
+    gen = torch.Generator().manual_seed(0)
+    src = torch.rand(50, 6, generator=gen)
+    tgt = torch.zeros(20, 6)
+    src_idx = torch.randperm(50, generator=gen)[:13]
+    tgt_idx = torch.randperm(20, generator=gen)[:13]
+    LimitBuffIndexCopyer(4).index_copy(0, src_idx, tgt_idx, src, tgt)
+    want = torch.zeros(20, 6)
+    want.index_copy_(0, tgt_idx, src.index_select(0, src_idx))
+    assert torch.equal(tgt, want)

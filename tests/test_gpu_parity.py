@@ -535,6 +535,78 @@ def test_two_window_protection_capacity_error():
     assert torch.equal(mgr.cached_idx_map[s].cpu(), torch.arange(20, 25))
 
 
+# ---------------------------------------------------------------------------------------------------- BASELINE configs
+def test_baseline_config0_plumbing_matches_oracle():
+    """BASELINE.json configs[0]: synthetic Kaggle-shape DLRM -- 26 tables x 1e5 rows, dim 16, batch 512 -- a few
+    training steps of the FreqAwareEmbeddingBag against the CPU oracle (exact maps, 1e-5 values)."""
+    ce = _mods()
+    import bench
+    F, rows, D, B = 26, 100_000, 16, 512
+    N = F * rows
+    gen = torch.Generator().manual_seed(1024)
+    weight = torch.empty(N, D).uniform_(-1.0 / N, 1.0 / N, generator=gen)
+    rows_t = torch.full((F,), rows, dtype=torch.long)
+    kw = dict(mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.01, warmup_ratio=0.7)
+    model = ce.FreqAwareEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=ce.EvictionStrategy.LFU, **kw)
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=OStrategy.LFU, **kw)
+    model.set_fused_optimizer("sgd", lr=1.0)
+    oopt = torch.optim.SGD(omodel.parameters(), lr=1.0)
+    offsets = torch.arange(F * B + 1)
+    for step in range(6):
+        ids = bench.sample_ids(rows_t, B, gen, "cpu")
+        grad = torch.randn(F * B, D, generator=gen) * 1e-3
+        out = model(ids.cuda(), offsets.cuda())
+        oout = omodel(ids, offsets)
+        close(out.cpu(), oout.detach())
+        out.backward(grad.cuda())
+        oout.backward(grad)
+        oopt.step(); oopt.zero_grad()
+        assert_maps_equal(model.cache_weight_mgr, omodel.cache_weight_mgr)
+    model.cache_weight_mgr.flush(); omodel.cache_weight_mgr.flush()
+    close(model.weight, omodel.weight)
+
+
+def test_baseline_config1_kaggle_full_size_properties():
+    """BASELINE.json configs[1]: Criteo-Kaggle shape at FULL size -- 33,762,577 rows x 128 (17.3 GB pinned host table,
+    GPU-initialised), cache_ratio 0.01, batch 4096 -- through size-independent properties."""
+    ce = _mods()
+    import bench
+    rows = bench.CRITEO_KAGGLE_ROWS
+    N, D, B, F = sum(rows), 128, 4096, len(rows)
+    model = ce.CachedEmbeddingBag(N, D, mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.01,
+                                  warmup_ratio=0.7, evict_strategy=ce.EvictionStrategy.LFU, init_seed=7)
+    mgr = model.cache_weight_mgr
+    assert mgr.cuda_row_num == 337_625 and tuple(model.weight.shape) == (N, D)
+    # GPU-side uniform init: right range, not constant
+    sample = model.weight[:: N // 1000]
+    assert float(sample.abs().max()) <= 1.0 / N and float(sample.std()) > 0
+    flat = model.weight.view(-1)
+    span = 4096 * 8192                    # rows 0 .. 262143: the hottest rows of the first tables live here
+    checksum = flat[:span].view(4096, 8192).sum(1, dtype=torch.float64).clone()
+    tail_checksum = flat[-span:].view(4096, 8192).sum(1, dtype=torch.float64).clone()
+    rows_t = torch.tensor(rows, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    offsets = torch.arange(F * B + 1, device="cuda")
+    model.set_fused_optimizer("sgd", lr=1.0)
+    touched = []
+    for it in range(6):
+        window = [bench.sample_ids(rows_t, B, gen, "cuda") for _ in range(4)]
+        slots = mgr.prepare_ids(torch.cat(window))
+        assert torch.equal(mgr._slot2row[slots].long(), torch.cat(window))        # id -> slot -> row round trip
+        occ = mgr._slot2row[mgr._slot2row >= 0]
+        assert occ.unique().numel() == occ.numel()                               # every row resident once
+        model.set_cache_op(False)
+        for ids, s in zip(window, torch.chunk(slots, 4)):
+            out = model(s, offsets)
+            assert torch.isfinite(out).all()
+            out.backward(torch.zeros_like(out))                                  # zero gradient: tables must not move
+        touched.append(torch.cat(window))
+    mgr.flush()
+    assert torch.equal(flat[:span].view(4096, 8192).sum(1, dtype=torch.float64), checksum)
+    assert torch.equal(flat[-span:].view(4096, 8192).sum(1, dtype=torch.float64), tail_checksum)
+    assert mgr.cuda_available_row_num == mgr.cuda_row_num
+
+
 # ---------------------------------------------------------------------------------------------------- full-size properties
 def test_large_table_round_trip_properties():
     """BASELINE-scale shapes through size-independent properties (the oracle would take minutes here):
