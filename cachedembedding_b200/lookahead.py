@@ -117,11 +117,11 @@ class LookaheadPrefetcher:
                 slot_ids = self.mgr.prepare_ids(ids_dev)
                 if offsets is not None and self.bag is not None:
                     # the gradient-independent half of every batch's fused backward also runs here, off the critical
-                    # path; torch.chunk gives the same views the training loop will pass to forward
+                    # path; splitting by the batches' own sizes gives the views the training loop passes to forward
                     if fence is not None and self.copy_stream is not None:
                         side.wait_event(fence)     # plan buffers of window k-1 are free again
                     offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
-                    for j, (chunk, off) in enumerate(zip(torch.chunk(slot_ids, len(parts)), offs)):
+                    for j, (chunk, off) in enumerate(zip(torch.split(slot_ids, [t.numel() for t in parts]), offs)):
                         self.bag.plan_backward(chunk, off, layout, layout_batch,
                                                workspace_factory=lambda n, p=parity, j=j: self._plan_buffer(p, j, n))
                 done = torch.cuda.Event()

@@ -105,8 +105,9 @@ def _columnwise_worker(rank, world, port, results):
 
 
 def _fused_exchange_worker(rank, world, port, results):
-    """Fused peer-memory exchange == NCCL all-to-all path, bit for bit on the pooled output, and within 1e-5 on the
-    tables after several steps with evictions."""
+    """Three ways through the same steps: (a) NCCL all-to-all, serial cache op (the reference's order); (b) exchange
+    fused into the kernels over peer memory; (c) fused exchange + look-ahead driver (windows of two batches, cache op
+    and backward plans on side streams).  Pooled outputs equal bit for bit, tables equal after flush, with evictions."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -115,61 +116,89 @@ def _fused_exchange_worker(rank, world, port, results):
     gen = torch.Generator().manual_seed(3)
     rows = [500, 40, 3000, 7, 1200]
     ranks = [0, 1, 1, 0, 1]
-    D, B = 128, 37                                   # B not divisible by the world
+    D, B, P, STEPS = 128, 37, 2, 8                   # B not divisible by the world
     weights = [torch.randn(n, D, generator=gen) * 0.1 for n in rows]
     mine = [t for t, r in enumerate(ranks) if r == rank]
-    bags = []
-    for fused in (False, True):
+    strides = [B // world + int(i < B % world) for i in range(world)]
+    # inputs of every step, drawn identically on all ranks (each keeps its own tables / its own batch rows)
+    steps = []
+    for step in range(STEPS):
+        per_table = []
+        for t in range(len(rows)):
+            lens = torch.randint(0, 3, (B,), generator=gen)
+            ids = (torch.rand(int(lens.sum()), generator=gen) ** 2 * rows[t]).long().clamp_(0, rows[t] - 1)
+            per_table.append((lens, ids))
+        grad = torch.randn(B, len(rows) * D, generator=gen)
+        local_off, parts, lens_all = 0, [], []
+        for t in mine:                               # local KJT: ids re-based to the local concatenated table (A.6)
+            lens, ids = per_table[t]
+            parts.append(ids + local_off); lens_all.append(lens); local_off += rows[t]
+        values = torch.cat(parts).cuda()
+        offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.cat(lens_all), 0)]).cuda()
+        steps.append((values, offsets, grad.split(strides, 0)[rank].cuda()))
+
+    def make_bag(fused):
         cfgs = [ce.TablewiseEmbeddingBagConfig(n, 0, assigned_rank=r, initial_weight=w.clone())
                 for n, r, w in zip(rows, ranks, weights)]
         bag = ce.ParallelCachedEmbeddingBagTablewise(cfgs, embedding_dim=D, include_last_offset=True, mode="sum",
-                                                     cache_ratio=0.2, warmup_ratio=1.0, sparse=True,   # cache starts full: every miss evicts
+                                                     cache_ratio=0.3, warmup_ratio=1.0, sparse=True,   # starts full
                                                      evict_strategy=ce.EvictionStrategy.LFU,
                                                      fused_optimizer="sgd", lr=0.25)
         bag.enable_fused_exchange(fused)
-        bags.append(bag)
-    strides = [B // world + int(i < B % world) for i in range(world)]
-    ok = True
-    for step in range(4):
-        # the local KJT: my tables only, ids already re-based to the local concatenated table (A.6)
-        local_off, parts, lens_all = 0, [], []
-        for t in mine:
-            lens = torch.randint(0, 3, (B,), generator=gen)
-            ids = (torch.rand(int(lens.sum()), generator=gen) ** 2 * rows[t]).long().clamp_(0, rows[t] - 1) + local_off
-            parts.append(ids); lens_all.append(lens); local_off += rows[t]
-        # every rank draws from the same generator stream: advance it for the other rank's tables too
-        for t in range(len(rows)):
-            if t not in mine:
-                lens = torch.randint(0, 3, (B,), generator=gen)
-                torch.rand(int(lens.sum()), generator=gen)
-        values = torch.cat(parts).cuda()
-        offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.cat(lens_all), 0)]).cuda()
-        grad = torch.randn(B, len(rows) * D, generator=gen)
-        my_grad = grad.split(strides, 0)[rank].cuda()
-        outs = []
-        for bag in bags:
+        return bag
+
+    outs = {}
+    bags = {}
+    for variant in ("nccl", "fused"):
+        bag = bags[variant] = make_bag(variant == "fused")
+        outs[variant] = []
+        for values, offsets, my_grad in steps:
             out = bag(values, offsets)
-            outs.append(out.detach().clone())
+            outs[variant].append(out.detach().clone())
             out.backward(my_grad)
-        if not torch.equal(outs[0], outs[1]):
+    # (c) look-ahead: windows of P batches
+    bag = bags["lookahead"] = make_bag(True)
+    bag.set_cache_op(False)
+    outs["lookahead"] = []
+    pf = ce.LookaheadPrefetcher(bag)
+    windows = [steps[w * P:(w + 1) * P] for w in range(STEPS // P)]
+    h = pf.submit([v for v, _, _ in windows[0]], offsets=[o for _, o, _ in windows[0]])
+    for w, win in enumerate(windows):
+        slots = h.wait()
+        sizes = [v.numel() for v, _, _ in win]
+        for s, (values, offsets, my_grad) in zip(torch.split(slots, sizes), win):
+            out = bag(s, offsets)
+            outs["lookahead"].append(out.detach().clone())
+            out.backward(my_grad)
+        pf.window_enqueued()
+        if w + 1 < len(windows):
+            h = pf.submit([v for v, _, _ in windows[w + 1]], offsets=[o for _, o, _ in windows[w + 1]])
+    pf.close()
+
+    ok = True
+    for variant in ("fused", "lookahead"):
+        for k in range(STEPS):
+            if not torch.equal(outs["nccl"][k], outs[variant][k]):
+                ok = False
+                print(f"[rank {rank}] {variant} step {k}: pooled outputs differ, max abs diff "
+                      f"{(outs['nccl'][k] - outs[variant][k]).abs().max().item():.3e}", flush=True)
+    for b in bags.values():
+        b.cache_weight_mgr.flush()
+    for variant in ("fused", "lookahead"):
+        if not torch.allclose(bags["nccl"].weight, bags[variant].weight, rtol=1e-5, atol=1e-6):
             ok = False
-            print(f"[rank {rank}] step {step}: pooled outputs differ, max abs diff "
-                  f"{(outs[0] - outs[1]).abs().max().item():.3e}", flush=True)
-    for bag in bags:
-        bag.cache_weight_mgr.flush()
-    if not torch.allclose(bags[0].weight, bags[1].weight, rtol=1e-5, atol=1e-6):
+            print(f"[rank {rank}] {variant}: tables differ, max abs diff "
+                  f"{(bags['nccl'].weight - bags[variant].weight).abs().max().item():.3e}", flush=True)
+    if not all(sum(b.num_write_back_history) > 0 for b in bags.values()):
         ok = False
-        print(f"[rank {rank}] tables differ, max abs diff {(bags[0].weight - bags[1].weight).abs().max().item():.3e}",
-              flush=True)
-    if not sum(bags[1].num_write_back_history) > 0:
-        ok = False
-        print(f"[rank {rank}] scenario did not evict", flush=True)
-    if torch.equal(bags[1].weight, torch.cat([weights[t] for t in mine])):
+        print(f"[rank {rank}] scenario did not evict: {[sum(b.num_write_back_history) for b in bags.values()]}", flush=True)
+    if torch.equal(bags["fused"].weight, torch.cat([weights[t] for t in mine])):
         ok = False
         print(f"[rank {rank}] table did not change", flush=True)
     results[rank] = bool(ok)
     dist.barrier()
-    bags[1].enable_fused_exchange(False)
+    for b in bags.values():
+        b.enable_fused_exchange(False)
     dist.destroy_process_group()
 
 
