@@ -107,7 +107,8 @@ def _columnwise_worker(rank, world, port, results):
 def _fused_exchange_worker(rank, world, port, results):
     """Three ways through the same steps: (a) NCCL all-to-all, serial cache op (the reference's order); (b) exchange
     fused into the kernels over peer memory; (c) fused exchange + look-ahead driver (windows of two batches, cache op
-    and backward plans on side streams).  Pooled outputs equal bit for bit, tables equal after flush, with evictions."""
+    and backward plans on side streams).  Pooled outputs equal bit for bit for (b) and within 1e-5 for (c), tables
+    equal within 1e-5 after flush, with evictions."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -178,7 +179,12 @@ def _fused_exchange_worker(rank, world, port, results):
     ok = True
     for variant in ("fused", "lookahead"):
         for k in range(STEPS):
-            if not torch.equal(outs["nccl"][k], outs[variant][k]):
+            # same slot assignment -> same summation grouping -> same bits.  The look-ahead driver protects two windows,
+            # picks other victims, so rows sit in other slots and the backward groups duplicate-slot partial sums
+            # differently: equal within fp32 rounding (1e-5 relative), not bit for bit.
+            same = torch.equal(outs["nccl"][k], outs[variant][k]) if variant == "fused" else \
+                torch.allclose(outs["nccl"][k], outs[variant][k], rtol=1e-5, atol=2e-6)
+            if not same:
                 ok = False
                 print(f"[rank {rank}] {variant} step {k}: pooled outputs differ, max abs diff "
                       f"{(outs['nccl'][k] - outs[variant][k]).abs().max().item():.3e}", flush=True)
