@@ -192,7 +192,7 @@ def run_b200(args):
     C_loc = min(N_loc, total_slots // world)
     K, W = args.steps, args.warmup
     total_steps = W + K
-    windows = (total_steps + P - 1) // P
+    windows = (total_steps + P - 1) // P + 1      # + the window the last timed one prefetches
 
     gen = torch.Generator(device=dev).manual_seed(SEED + rank)
     rows_dev = torch.tensor(rows_loc, dtype=torch.long, device=dev)
@@ -245,55 +245,64 @@ def run_b200(args):
         out.backward(grad_holder["g"])
         return out
 
-    def window_ids(w, host_inputs, batches):
-        src = host_batches if host_inputs else batches
-        return src[w * P:(w + 1) * P]
+    class Runner:
+        """Steps of one arm, in order.  With the look-ahead driver the pipeline stays primed across calls: when the last
+        step of window w has been enqueued, window w+1 is submitted to the side streams -- also at the end of a call, so
+        the first window of the NEXT call (the timed one after the warm-up) was prepared under the previous window's
+        compute exactly as in steady state; every timed step still carries 1/P of one prepare_ids (for a later window)."""
 
-    def run_steps(first, count, host_inputs, batches=None, overlap=overlap):
-        """Steps [first, first+count).  host_inputs: ids start in pinned host memory and are copied H2D inside the
-        region (every batch of a window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row is
-        read back D2H per step.  With overlap the prepare_ids of window w+1 runs on a side stream under window w."""
-        h2d = d2h = 0
-        last = first + count
-        w_first, w_last = first // P, (last - 1) // P
-        pf = prefetcher["pf"] if overlap else None
-        saved_protect = mgr.protect_windows
-        if not overlap:
-            mgr.protect_windows = 1          # reference order: only the current window is protected
-        plan = dict(offsets=offsets) if not args.no_plan_side else {}
-        handle = pf.submit(window_ids(w_first, host_inputs, batches), **plan) if overlap else None
-        for w in range(w_first, w_last + 1):
-            if overlap:
-                slots_window = torch.chunk(handle.wait(), P)
-            else:
-                win = torch.cat([b.to(dev, non_blocking=True) for b in window_ids(w, host_inputs, batches)])
-                slots_window = torch.chunk(mgr.prepare_ids(win), P)
-            if host_inputs:
-                h2d += P * n_b * 8
-            for j in range(P):
-                s = w * P + j
-                if s < first or s >= last:
-                    continue
-                out = embed_step(slots_window[j])
-                if host_inputs:
+        def __init__(self, batches, host_inputs, overlap=overlap):
+            self.batches, self.host, self.overlap = batches, host_inputs, overlap
+            self.w, self.slots, self.next_w, self.next = -1, None, -1, None
+            self.plan = dict(offsets=offsets) if not args.no_plan_side else {}
+
+        def ids(self, w):
+            return self.batches[w * P:(w + 1) * P]
+
+        def run(self, first, count):
+            """Steps [first, first+count).  host inputs: ids start in pinned host memory and are copied H2D inside the
+            region (every batch of a window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row
+            is read back D2H per step."""
+            h2d = d2h = 0
+            pf = prefetcher["pf"] if self.overlap else None
+            saved_protect = mgr.protect_windows
+            if not self.overlap:
+                mgr.protect_windows = 1          # reference order: only the current window is protected
+            for s in range(first, first + count):
+                w, j = divmod(s, P)
+                if w != self.w:                  # entering a new window
+                    if self.overlap:
+                        if self.next_w != w:
+                            self.next, self.next_w = pf.submit(self.ids(w), **self.plan), w
+                            h2d += P * n_b * 8 if self.host else 0
+                        self.slots = torch.chunk(self.next.wait(), P)
+                    else:
+                        win = torch.cat([b.to(dev, non_blocking=True) for b in self.ids(w)])
+                        h2d += P * n_b * 8 if self.host else 0
+                        self.slots = torch.chunk(mgr.prepare_ids(win), P)
+                    self.w = w
+                out = embed_step(self.slots[j])
+                if self.host:
                     result_host.copy_(out.view(-1)[:D], non_blocking=True)
                     d2h += D * 4
-            if overlap:
-                pf.window_enqueued()
-                if w < w_last:
-                    handle = pf.submit(window_ids(w + 1, host_inputs, batches), **plan)
-        if overlap:
-            pf.drain()
-        mgr.protect_windows = saved_protect
-        return h2d, d2h
+                if self.overlap and j == P - 1 and (w + 1) * P < len(self.batches):
+                    pf.window_enqueued()
+                    self.next, self.next_w = pf.submit(self.ids(w + 1), **self.plan), w + 1
+                    h2d += P * n_b * 8 if self.host else 0
+            mgr.protect_windows = saved_protect
+            return h2d, d2h
 
-    def timed(first, count, host_inputs, batches=None):
+        def finish(self):
+            if self.overlap:
+                prefetcher["pf"].drain()
+
+    def timed(runner, first, count):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        h2d, d2h = run_steps(first, count, host_inputs, batches)
+        h2d, d2h = runner.run(first, count)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -307,8 +316,9 @@ def run_b200(args):
     # warm-up is rounded to whole windows internally only for the *slot* bookkeeping: steps W..W+K-1 are timed.
     # two untimed windows on scratch ids before anything is measured: first-touch costs of the caching allocator
     # (cross-stream buffers of the look-ahead driver) and of the lazily created streams/events
-    scratch = [sample_ids(rows_dev, B, gen, dev) for _ in range(2 * P)]
-    run_steps(0, 2 * P, False, scratch)
+    scratch = Runner([sample_ids(rows_dev, B, gen, dev) for _ in range(3 * P)], False)
+    scratch.run(0, 2 * P)
+    scratch.finish()
     del scratch
     if world > 1 and getattr(model, "_exchange", None) is not None:
         # the "dense part" leaves its gradient where the fused backward reads it (no staging copy per step)
@@ -318,10 +328,12 @@ def run_b200(args):
     # clocks are sampled from the warm-up to the end of the end-to-end arm: every arm runs the same steps, and the
     # K timed steps alone are shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local) if rank == 0 else None
-    run_steps(0, W, False, arms["value"])
+    value_runner = Runner(arms["value"], False)
+    value_runner.run(0, W)
     launches0 = _lib.launch_count()
     hist0 = len(mgr.num_miss_history)
-    ms_total, _, _ = timed(W, K, False, arms["value"])
+    ms_total, _, _ = timed(value_runner, W, K)
+    value_runner.finish()
     gpu_launches = _lib.launch_count() - launches0
     miss_u = sum(mgr.num_miss_history[hist0:])
     hit_u = sum(mgr.num_hits_history[hist0:])
@@ -331,7 +343,7 @@ def run_b200(args):
     # ---- per-kernel timers on a replay of the same steps (CUDA events on the launching stream) ------------------
     # (look-ahead off for this replay: every kernel is alone on the GPU, so its event-bracketed time is its own)
     _lib.profile_enable(True)
-    run_steps(W, K, False, arms["profile"], overlap=False)
+    Runner(arms["profile"], False, overlap=False).run(W, K)
     torch.cuda.synchronize()
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
@@ -339,8 +351,10 @@ def run_b200(args):
     # ---- end-to-end arm: ids come from pinned host memory, one pooled row goes back per step ---------------------
     host_batches = [b.cpu().pin_memory() for b in arms["e2e"]]
     result_host = torch.empty(D, dtype=torch.float32).pin_memory()
-    run_steps(0, W, True)
-    e2e_ms, h2d, d2h = timed(W, K, True)
+    e2e_runner = Runner(host_batches, True)
+    e2e_runner.run(0, W)
+    e2e_ms, h2d, d2h = timed(e2e_runner, W, K)
+    e2e_runner.finish()
     clocks = sampler.stop() if sampler else None
 
     if prefetcher["pf"] is not None:
@@ -390,7 +404,9 @@ def run_b200(args):
         "config": {
             "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
                         f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
-            "lookahead": "prepare_ids(window k+1) on a side stream under window k" if overlap else "serial (reference order)",
+            "lookahead": ("prepare_ids(window k+1) on side streams under window k; the pipeline stays primed across the "
+                          "warm-up/timed boundary (each timed step carries 1/P of one prepare_ids)") if overlap
+            else "serial (reference order)",
             "tables_per_rank": [sum(1 for a in arrange if a == q) for q in range(world)],
             "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
             "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
