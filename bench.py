@@ -13,8 +13,11 @@ loop of /root/reference/recsys/dlrm_main.py:235-279 restricted to the embedding 
 Workload at N = 1: BASELINE.json configs[2] -- Criteo-1TB DLRM shape (26 tables, 177,944,275 rows, dim 128, the full
 91.1 GB fp32 table pinned in host DRAM), cache_ratio 0.01, prefetch_num 8, batch 65536 -- whenever the host has the RAM
 for it; otherwise the rows are scaled down and `config.row_scale` says by how much.
-N > 1: the same tables sharded table-wise over the ranks (BASELINE.json configs[3]), global batch 65536, one all-to-all
-of pooled embeddings forward and of their gradients backward ("strong" scaling: total work is fixed).
+N > 1: the same tables sharded table-wise over the ranks (BASELINE.json configs[3]), global batch 65536 ("strong"
+scaling: total work is fixed); the all-to-all of pooled embeddings and of their gradients is fused into the forward /
+backward kernels over NVLink peer memory (--no-fused-exchange: NCCL all-to-all, the reference's way).
+By default the cache operation of window k+1 runs on side streams under the compute of window k (look-ahead driver,
+--no-overlap for the reference's serial order).  `--impl reference` times the CPU oracle port on the host cores.
 """
 from __future__ import annotations
 
@@ -155,7 +158,7 @@ def run_b200(args):
     import torch.distributed as dist
     import cachedembedding_b200 as ce
     from cachedembedding_b200 import _lib
-    from cachedembedding_b200.collectives import dual_all_to_all_tablewise, split_sizes
+    from cachedembedding_b200.collectives import split_sizes
 
     rank, local, world = dist_info()
     assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
