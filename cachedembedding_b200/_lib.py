@@ -12,10 +12,12 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
+PREPARE_PENDING = -1
+STATE_AVAIL, STATE_EPOCH, STATE_CALLS, STATE_WORDS = 0, 1, 2, 8
 EVICT_LFU, EVICT_DATASET = 1, 2
 MODE_SUM, MODE_MEAN = 0, 1
 OPT_SGD, OPT_ROWWISE_ADAGRAD = 0, 1
@@ -31,8 +33,8 @@ EXPORTS = (
     "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
     "cebag_host_device_pointer", "cebag_fill_uniform",
     "cebag_device_alloc", "cebag_device_free", "cebag_ipc_export", "cebag_ipc_import", "cebag_ipc_close",
-    "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_flush", "cebag_preload",
-    "cebag_admit_row", "cebag_evict_slot",
+    "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_prepare_ids_async", "cebag_prepare_result_status",
+    "cebag_flush", "cebag_preload", "cebag_admit_row", "cebag_evict_slot", "cebag_available_rows",
     "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused", "cebag_bag_backward_plan",
     "cebag_bag_backward_coo", "cebag_bag_backward_dense", "cebag_bag_backward_weights",
 )
@@ -48,23 +50,31 @@ class CacheCapacityError(AssertionError, CebagError):
 
 class Table(Structure):
     _fields_ = [
-        ("num_rows", c_int64), ("dim", c_int32), ("cache_rows", c_int32), ("strategy", c_int32), ("epoch", c_int32),
-        ("protect_windows", c_int32), ("reserved0", c_int32),
-        ("avail", c_int64),
+        ("num_rows", c_int64), ("dim", c_int32), ("cache_rows", c_int32), ("strategy", c_int32),
+        ("protect_windows", c_int32),
         ("host_table", c_void_p), ("host_state", c_void_p), ("cache", c_void_p), ("cache_state", c_void_p),
         ("idx_map", c_void_p), ("row2slot", c_void_p), ("slot2row", c_void_p), ("freq", c_void_p),
-        ("slot_epoch", c_void_p), ("miss_bitmap", c_void_p),
+        ("slot_epoch", c_void_p), ("miss_bitmap", c_void_p), ("hit_bitmap", c_void_p), ("dev_state", c_void_p),
     ]
 
 
 class Workspace(Structure):
     _fields_ = [("device", c_void_p), ("device_bytes", c_size_t), ("pinned", c_void_p),
-                ("copy_stream", c_void_p), ("copy_done_event", c_void_p)]
+                ("copy_stream", c_void_p), ("copy_done_event", c_void_p), ("writeback_done_event", c_void_p),
+                ("victims_ready_event", c_void_p), ("stage", c_void_p), ("stage_state", c_void_p),
+                ("stage_rows", c_int64)]
 
 
 class PrepareStats(Structure):
     _fields_ = [("unique_hits", c_int64), ("unique_misses", c_int64), ("evicted", c_int64),
                 ("miss_lookups", c_int64), ("total_lookups", c_int64)]
+
+
+class PrepareResult(Structure):
+    """Device-written record of one cebag_prepare_ids_async call (pinned, device-mapped host memory)."""
+    _fields_ = [("status", c_int64), ("unique_hits", c_int64), ("unique_misses", c_int64), ("evicted", c_int64),
+                ("miss_lookups", c_int64), ("total_lookups", c_int64), ("evictable", c_int64),
+                ("avail_after", c_int64)]
 
 
 class Exchange(Structure):
@@ -114,6 +124,10 @@ def _declare(lib):
     lib.cebag_prepare_workspace_bytes.restype = c_size_t
     lib.cebag_prepare_ids.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),
                                       POINTER(PrepareStats), c_void_p]
+    lib.cebag_prepare_ids_async.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),
+                                            c_void_p, c_void_p]
+    lib.cebag_prepare_result_status.argtypes = [POINTER(Table), c_void_p, POINTER(PrepareStats)]
+    lib.cebag_available_rows.argtypes = [POINTER(Table), POINTER(c_int64), c_void_p]
     lib.cebag_flush.argtypes = [POINTER(Table), POINTER(Workspace), POINTER(c_int64), c_void_p]
     lib.cebag_preload.argtypes = [POINTER(Table), c_void_p, c_void_p, c_int64, c_void_p]
     lib.cebag_admit_row.argtypes = [POINTER(Table), c_int64, c_int64, c_void_p]
@@ -186,5 +200,5 @@ def check(rc: int):
     raise CebagError(msg)
 
 
-__all__ = ["load", "check", "last_error", "Table", "Workspace", "PrepareStats", "BagArgs", "byref", "CebagError",
+__all__ = ["load", "check", "last_error", "Table", "Workspace", "PrepareStats", "PrepareResult", "BagArgs", "byref", "CebagError",
            "CacheCapacityError", "EXPORTS", "LIB_PATH"]

@@ -7,9 +7,12 @@ single-row helpers), same attributes (``cuda_cached_weight``, ``weight``, ``idx_
 ``inverted_cached_idx``, ``freq_cnter``, hit/miss histories).  What differs is how the work is done:
 
 * the maps are int32 on the device (``cached_idx_map`` & co. are int64 *views* materialised on access);
-* ``prepare_ids`` is one C call that enqueues hand-written kernels (no sort-based unique/isin/topk) and moves rows
-  between the pinned host table and HBM with zero-copy 128-bit accesses from the GPU (no CPU gather/scatter, no staging
-  buffer, both PCIe directions at once);
+* ``prepare_ids`` is one C call that only ENQUEUES hand-written kernels (no sort-based unique/isin/topk, no wait for
+  the GPU inside the call: misses, evictions and free slots are counted in device memory) and moves rows between the
+  pinned host table and HBM with zero-copy 128-bit accesses from the GPU (no CPU gather/scatter);
+* with ``async_copy`` (``set_cache_mgr_async_copy(True)``, reference flag ``--use_cache_mgr_async_copy``) the PCIe row
+  traffic runs on a private copy stream: victims are parked in an HBM staging buffer, the missed rows are filled, and
+  the write-back to the host table goes on under the following forward/backward steps;
 * there is no CPU path: constructing a manager without a CUDA device raises.
 """
 from __future__ import annotations
@@ -17,6 +20,7 @@ from __future__ import annotations
 import ctypes
 import sys
 import time
+from collections import deque
 from typing import List, Optional
 
 import numpy as np
@@ -26,6 +30,9 @@ import torch.nn as nn
 from . import _lib
 from ._lib import CacheCapacityError  # noqa: F401  (re-export)
 from .evict_strategy import EvictionStrategy
+
+
+_RESULT_RING = 64     # result records of prepare_ids calls that may be in flight at once
 
 
 def _stream_ptr() -> int:
@@ -62,8 +69,9 @@ class CachedParamMgr(nn.Module):
     """Manage an embedding table whose rows live in host DRAM with a fixed number of them cached in HBM.
 
     Args mirror upstream (A.1): ``weight`` is the host table fp32[N, D]; ``cuda_row_num`` the number of HBM slots.
-    ``buffer_size`` is accepted for API compatibility: the reference used it to bound the staging buffer of its
-    chunked copier (A.7); rows here move without any staging buffer, so there is nothing to bound.
+    ``buffer_size`` is accepted for API compatibility: the reference used it to bound the host staging buffer of its
+    chunked copier (A.7); rows here move between the pinned table and HBM without host staging, so there is nothing
+    to bound.
     ``with_row_state`` adds one fp32 per row (row-wise Adagrad accumulator) that travels with the row.
     """
 
@@ -122,16 +130,34 @@ class CachedParamMgr(nn.Module):
             self.row_state = None
             self._state_pin = None
             self.cuda_cached_state = None
-        self._epoch = 0
+        self.register_buffer("_hit_bitmap", torch.zeros((C + 31) // 32, dtype=torch.int32, device=dev),
+                             persistent=False)
+        state = torch.zeros(_lib.STATE_WORDS, dtype=torch.int64)
+        state[_lib.STATE_AVAIL] = C
+        self.register_buffer("_dev_state", state.to(dev), persistent=False)
         self.protect_windows = 1      # 2 while a LookaheadPrefetcher overlaps prepare_ids with the previous window
-        self._copy_stream = None      # set by the look-ahead driver: row copies of prepare_ids go to this stream
-        self._copy_done = None        # event recorded after them
+        # stream plumbing of the row traffic (see _workspace)
+        self._copy_stream = None      # a look-ahead driver's copy stream, for the calls it makes
+        self._own_copy_stream = None  # created on first use when async_copy is on
+        self._victims_ready = None    # event the victims' rows have to wait for (set by the look-ahead driver)
+        self._rows_ready = None       # event after the last fill on a copy stream: the next forward waits for it
+        self._last_writeback = None   # event after the last write-back on a copy stream: flush waits for it
+        self._defer_results = False   # look-ahead driver: results are read when the window is waited for
+        self.stage_rows = 0           # 0: max(65536, C // 4) rows, capped at C
+        self._ws_ring = [None, None, None]       # [buffer, event after the call, write-back event]
+        self._ws_next = 0
+        self._stage_ring = [None, None]          # [rows, state, write-back event]
+        self._stage_next = 0
+        self._results = torch.full((_RESULT_RING, 8), -1, dtype=torch.int64).pin_memory()
+        self._result_next = 0
+        self._pending = deque()       # (result index, event, n): calls whose result has not been read yet
         self._counters_pinned = torch.zeros(64, dtype=torch.int32).pin_memory()
+        self._calls = 0
 
         self.evict_backlist = torch.tensor([], device=dev)
-        self.num_hits_history: List[int] = []
-        self.num_miss_history: List[int] = []
-        self.num_write_back_history: List[int] = []
+        self._num_hits_history: List[int] = []
+        self._num_miss_history: List[int] = []
+        self._num_write_back_history: List[int] = []
         self._cpu_to_cuda_numel = 0
         self._cuda_to_cpu_numel = 0
         self._cache_miss = 0
@@ -145,9 +171,7 @@ class CachedParamMgr(nn.Module):
         t.dim = self.embedding_dim
         t.cache_rows = self.cuda_row_num
         t.strategy = _lib.EVICT_LFU if self._evict_strategy == EvictionStrategy.LFU else _lib.EVICT_DATASET
-        t.epoch = self._epoch
         t.protect_windows = self.protect_windows
-        t.avail = self._cuda_available_row_num
         t.host_table = self._pin.device_ptr
         t.host_state = self._state_pin.device_ptr if self._state_pin is not None else None
         t.cache = self.cuda_cached_weight.data_ptr()
@@ -158,21 +182,130 @@ class CachedParamMgr(nn.Module):
         t.freq = self._freq.data_ptr() if self._freq is not None else None
         t.slot_epoch = self._slot_epoch.data_ptr()
         t.miss_bitmap = self._miss_bitmap.data_ptr()
+        t.hit_bitmap = self._hit_bitmap.data_ptr()
+        t.dev_state = self._dev_state.data_ptr()
         return t
 
-    def _sync_from(self, t: _lib.Table):
-        self._epoch = t.epoch
-        self._cuda_available_row_num = int(t.avail)
+    def _refresh_avail(self):
+        """Free slots after an operation that changed them outside prepare_ids (waits for the stream)."""
+        t = self._table()
+        avail = ctypes.c_int64(0)
+        _lib.check(self._lib.cebag_available_rows(ctypes.byref(t), ctypes.byref(avail), _stream_ptr()))
+        self._cuda_available_row_num = int(avail.value)
+
+    def _active_copy_stream(self):
+        """Where the PCIe row traffic of the next prepare_ids goes: the look-ahead driver's copy stream, the
+        manager's own one when async_copy is on, or None (= the calling stream, the reference's serial order)."""
+        if self._copy_stream is not None:
+            return self._copy_stream
+        if self._async_copy:
+            if self._own_copy_stream is None:
+                self._own_copy_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            return self._own_copy_stream
+        return None
 
     def _workspace(self, t: _lib.Table, n_ids: int):
+        """Scratch + stream plumbing of one call.  Buffers come from small rings owned by the manager (nothing is
+        allocated per call in steady state); a buffer is handed out again only after the calling stream has been made
+        to wait for the kernels -- on either stream -- that still read it."""
+        cur = torch.cuda.current_stream()
         nbytes = int(self._lib.cebag_prepare_workspace_bytes(ctypes.byref(t), n_ids))
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        ws = _lib.Workspace(buf.data_ptr(), nbytes, self._counters_pinned.data_ptr(), None, None)
-        if self._copy_stream is not None and self._copy_done is not None:
-            ws.copy_stream = self._copy_stream.cuda_stream
-            ws.copy_done_event = self._copy_done.cuda_event
-            buf.record_stream(self._copy_stream)       # the copy kernels read their row lists from this buffer
-        return ws, buf
+        i = self._ws_next
+        self._ws_next = (i + 1) % len(self._ws_ring)
+        entry = self._ws_ring[i]
+        if entry is not None:
+            for ev in entry[1:]:
+                if ev is not None:
+                    cur.wait_event(ev)
+        if entry is None or entry[0].numel() < nbytes:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        else:
+            buf = entry[0]
+        ws = _lib.Workspace(buf.data_ptr(), buf.numel(), self._counters_pinned.data_ptr(), None, None, None, None,
+                            None, None, 0)
+        entry = [buf, None, None]
+        self._ws_ring[i] = entry
+        cstream = self._active_copy_stream()
+        events = None
+        if cstream is not None:
+            rows_done, wb_done = torch.cuda.Event(), torch.cuda.Event()
+            rows_done.record(cstream)          # instantiates the events; re-recorded by the library after the copies
+            wb_done.record(cstream)
+            ws.copy_stream = cstream.cuda_stream
+            ws.copy_done_event = rows_done.cuda_event
+            ws.writeback_done_event = wb_done.cuda_event
+            entry[2] = wb_done
+            events = (rows_done, wb_done)
+            # staging buffer for the victims (double-buffered: the write-back of the previous call may still read its own)
+            C, D = self.cuda_row_num, self.embedding_dim
+            rows = self.stage_rows if self.stage_rows > 0 else max(65536, C // 4)
+            rows = min(rows, C)
+            j = self._stage_next
+            self._stage_next = (j + 1) % len(self._stage_ring)
+            st = self._stage_ring[j]
+            if st is not None and st[2] is not None:
+                cur.wait_event(st[2])
+            if st is None or st[0].shape[0] != rows:
+                st = [torch.empty(rows, D, dtype=torch.float32, device=self.device),
+                      torch.empty(rows, dtype=torch.float32, device=self.device) if self.with_row_state else None, None]
+            st[2] = wb_done
+            self._stage_ring[j] = st
+            ws.stage = st[0].data_ptr()
+            ws.stage_state = st[1].data_ptr() if st[1] is not None else None
+            ws.stage_rows = rows
+        if self._victims_ready is not None:
+            ws.victims_ready_event = self._victims_ready.cuda_event
+        return ws, entry, events
+
+    # ---- results of the asynchronous calls -----------------------------------------------------------------------------
+    def _harvest(self, block: bool = True):
+        """Read the result records of finished prepare_ids calls (all of them if `block`): histories and counters are
+        updated in call order; a rejected call raises here (CacheCapacityError / IndexError)."""
+        while self._pending:
+            idx, ev, n = self._pending[0]
+            if not block and not ev.query():
+                break
+            ev.synchronize()
+            self._pending.popleft()
+            rec = self._results[idx]
+            t = self._table()
+            stats = _lib.PrepareStats()
+            rc = self._lib.cebag_prepare_result_status(ctypes.byref(t), rec.data_ptr(), ctypes.byref(stats))
+            _lib.check(rc)
+            self._cuda_available_row_num = int(rec[7])
+            self._cache_miss += stats.miss_lookups
+            self._total_cache += n
+            self._num_hits_history.append(int(stats.unique_hits))
+            self._num_miss_history.append(int(stats.unique_misses))
+            self._num_write_back_history.append(int(stats.evicted))
+            self._cpu_to_cuda_numel += stats.unique_misses * self.embedding_dim
+            self._cuda_to_cpu_numel += stats.evicted * self.embedding_dim
+
+    @property
+    def num_hits_history(self) -> List[int]:
+        self._harvest()
+        return self._num_hits_history
+
+    @property
+    def num_miss_history(self) -> List[int]:
+        self._harvest()
+        return self._num_miss_history
+
+    @property
+    def num_write_back_history(self) -> List[int]:
+        self._harvest()
+        return self._num_write_back_history
+
+    def wait_rows(self):
+        """Make the current stream wait for the last fill that ran on a copy stream (no-op otherwise)."""
+        if self._rows_ready is not None:
+            torch.cuda.current_stream().wait_event(self._rows_ready)
+            self._rows_ready = None
+
+    def _wait_writeback(self):
+        if self._last_writeback is not None:
+            torch.cuda.current_stream().wait_event(self._last_writeback)
+            self._last_writeback = None
 
     # ---- reference-compatible views of the maps (int64, like upstream's buffers) ------------------------------------
     @property
@@ -187,7 +320,7 @@ class CachedParamMgr(nn.Module):
 
     @property
     def inverted_cached_idx(self) -> torch.Tensor:
-        return self._row2slot.long()
+        return self._row2slot.long().clamp_(min=-1)
 
     @property
     def freq_cnter(self) -> torch.Tensor:
@@ -197,6 +330,7 @@ class CachedParamMgr(nn.Module):
 
     @property
     def cuda_available_row_num(self) -> int:
+        self._harvest()
         return self._cuda_available_row_num
 
     def cpu_weight_data(self, row_idx: int) -> torch.Tensor:
@@ -235,20 +369,23 @@ class CachedParamMgr(nn.Module):
             _lib.check(self._lib.cebag_preload(ctypes.byref(t), rows.data_ptr(),
                                                freq_init.data_ptr() if freq_init is not None else None,
                                                preload, _stream_ptr()))
-            self._sync_from(t)
-            torch.cuda.current_stream().synchronize()   # rows / freq_init are locals
+            self._refresh_avail()                        # waits for the stream: rows / freq_init are locals
 
     # ---- A.1 flush ------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def flush(self):
         """Write every resident row back to the host table and empty the cache."""
+        self._harvest()
+        self.wait_rows()
+        self._wait_writeback()
         t = self._table()
-        ws, buf = self._workspace(t, 1)
+        ws, entry, _ = self._workspace(t, 1)
         written = ctypes.c_int64(0)
         _lib.check(self._lib.cebag_flush(ctypes.byref(t), ctypes.byref(ws), ctypes.byref(written), _stream_ptr()))
-        self._sync_from(t)
+        if self._own_copy_stream is not None:
+            self._own_copy_stream.synchronize()
+        self._cuda_available_row_num = self.cuda_row_num
         self._cuda_to_cpu_numel += written.value * self.embedding_dim
-        assert self._cuda_available_row_num == self.cuda_row_num
         return written.value
 
     # ---- A.3 prepare_ids --------------------------------------------------------------------------------------------------
@@ -264,27 +401,41 @@ class CachedParamMgr(nn.Module):
         ids = ids.to(device=self.device, dtype=torch.long).contiguous().view(-1)
         n = ids.numel()
         out = torch.empty_like(ids)
+        self._calls += 1
+        if self._calls >= 2**31 - 64:                 # the window stamps are int32
+            self._reset_stamps()
         t = self._table()
-        ws, buf = self._workspace(t, n)
-        stats = _lib.PrepareStats()
-        rc = self._lib.cebag_prepare_ids(ctypes.byref(t), ids.data_ptr(), n, out.data_ptr(), ctypes.byref(ws),
-                                         ctypes.byref(stats), _stream_ptr())
-        self._sync_from(t)
+        ws, entry, copy_events = self._workspace(t, n)
+        idx = self._result_next
+        self._result_next = (idx + 1) % _RESULT_RING
+        if len(self._pending) >= _RESULT_RING - 1:
+            self._harvest()
+        rec = self._results[idx]
+        rc = self._lib.cebag_prepare_ids_async(ctypes.byref(t), ids.data_ptr(), n, out.data_ptr(), ctypes.byref(ws),
+                                               rec.data_ptr(), _stream_ptr())
         _lib.check(rc)
-        self._cache_miss += stats.miss_lookups
-        self._total_cache += n
-        self.num_hits_history.append(int(stats.unique_hits))
-        self.num_miss_history.append(int(stats.unique_misses))
-        self.num_write_back_history.append(int(stats.evicted))
-        self._cpu_to_cuda_numel += stats.unique_misses * self.embedding_dim
-        self._cuda_to_cpu_numel += stats.evicted * self.embedding_dim
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        entry[1] = done
+        self._pending.append((idx, done, n))
+        if copy_events is not None:
+            self._rows_ready, self._last_writeback = copy_events
+        if not self._defer_results:
+            self._harvest()       # the reference raises its capacity assert from this call
         self._elapsed_dict["cache_op"] += time.perf_counter() - start
         return out
+
+    def _reset_stamps(self):
+        torch.cuda.synchronize(self.device)
+        self._harvest()
+        self._slot_epoch.zero_()
+        self._dev_state[_lib.STATE_EPOCH] = 0
+        self._calls = 0
 
     def _id_to_cached_cuda_id(self, ids: torch.Tensor) -> torch.Tensor:
         ids = ids.to(self.device).view(-1)
         rows = ids if self._idx_map is None else self._idx_map[ids].long()
-        return self._row2slot[rows].long()
+        return self._row2slot[rows].long().clamp_(min=-1)
 
     @torch.no_grad()
     def _prepare_rows_on_cuda(self, cpu_row_idxs: torch.Tensor) -> None:
@@ -298,22 +449,23 @@ class CachedParamMgr(nn.Module):
             ids = inv[rows].long()
         else:
             ids = rows
+        self._harvest()
         hits, misses, wb = len(self.num_hits_history), len(self.num_miss_history), len(self.num_write_back_history)
         freq_before = self._freq.clone() if self._freq is not None else None
         resident_before = self._row2slot[rows] >= 0
         slots = self.prepare_ids(ids)
         # this entry point is not a lookup: undo prepare_ids' bookkeeping (histories, LFU counts of the ids)
-        del self.num_hits_history[hits:], self.num_miss_history[misses:], self.num_write_back_history[wb:]
+        del self._num_hits_history[hits:], self._num_miss_history[misses:], self._num_write_back_history[wb:]
         if self._freq is not None:
             freq_before[slots[~resident_before]] = 0      # A.4 step 6: admitted slots start at 0
             self._freq.copy_(freq_before)
 
     # ---- legacy single-row helpers (upstream test_cachemgr, B.1) ------------------------------------------------------------
     def _row_in_cuda(self, row_id: int) -> bool:
-        return bool(self._row2slot[row_id].item() != -1)
+        return bool(self._row2slot[row_id].item() >= 0)
 
     def _find_free_cuda_row(self) -> int:
-        if self._cuda_available_row_num == 0:
+        if self.cuda_available_row_num == 0:
             return -1
         return int(torch.nonzero(self._slot2row == -1).squeeze(1)[0].item())
 
@@ -325,7 +477,7 @@ class CachedParamMgr(nn.Module):
             raise RuntimeError("Can not evict a row")
         t = self._table()
         _lib.check(self._lib.cebag_evict_slot(ctypes.byref(t), int(slot.item()), _stream_ptr()))
-        self._sync_from(t)
+        self._refresh_avail()
         self._cuda_to_cpu_numel += self.embedding_dim
         return int(slot.item())
 
@@ -336,11 +488,12 @@ class CachedParamMgr(nn.Module):
             slot = self._evict()
         t = self._table()
         _lib.check(self._lib.cebag_admit_row(ctypes.byref(t), int(row_id), slot, _stream_ptr()))
-        self._sync_from(t)
+        self._refresh_avail()
         self._cpu_to_cuda_numel += self.embedding_dim
 
     # ---- statistics ------------------------------------------------------------------------------------------------------------
     def print_comm_stats(self):
+        self._harvest()
         elapsed = max(self._elapsed_dict["cache_op"], 1e-12)
         mb_out = self._cuda_to_cpu_numel * self.elem_size_in_byte / 1e6
         mb_in = self._cpu_to_cuda_numel * self.elem_size_in_byte / 1e6

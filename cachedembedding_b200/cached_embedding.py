@@ -262,12 +262,13 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
 
     # ---- backward plans (look-ahead) ----------------------------------------------------------------------------------------
     def plan_backward(self, slot_ids: torch.Tensor, offsets: torch.Tensor, layout="bag_major", layout_batch=0,
-                      workspace_factory=None) -> bool:
+                      workspace_factory=None, tag=None) -> bool:
         """Run the gradient-independent half of the fused backward (lookup->bag map + radix sort by slot) for a batch NOW,
-        on the current stream, and keep it until the backward of a forward over the very same `slot_ids` tensor picks it
-        up.  A look-ahead driver calls this on its side stream right after prepare_ids (`workspace_factory(nbytes)` lets
-        it supply a recycled buffer).  Returns False (and does nothing) when the fused backward is off or the bag is not
-        in plain mode 'sum'."""
+        on the current stream, and keep it until the backward of a forward over the very same `slot_ids` / `offsets`
+        tensors picks it up.  A look-ahead driver calls this on its side stream right after prepare_ids
+        (`workspace_factory(nbytes)` lets it supply a recycled buffer, `tag` names the group of plans that is dropped
+        together when the buffers are recycled).  Returns False (and does nothing) when the fused backward is off or
+        the bag is not in plain mode 'sum'."""
         if self._fused_optimizer is None or self.mode != "sum" or slot_ids.dim() != 1:
             return False
         lib = _lib.load()
@@ -285,8 +286,18 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         _lib.check(lib.cebag_bag_backward_plan(ctypes.byref(a), ws.data_ptr(), nbytes, _stream_ptr()))
         if not hasattr(self, "_bwd_plans"):
             self._bwd_plans = {}
-        self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = (ws, offsets.data_ptr(), nbytes)
+        # the plan is only valid for these very tensors: keep them alive so that their addresses cannot be recycled
+        self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = (ws, offsets.data_ptr(), nbytes, tag, slot_ids, offsets)
         return True
+
+    def drop_backward_plans(self, tag=None):
+        """Forget plans that were never consumed (all of them, or the group `tag`): their workspace is about to be
+        reused, or the batches they were made for will not run a backward."""
+        plans = getattr(self, "_bwd_plans", None)
+        if not plans:
+            return
+        for key in [k for k, v in plans.items() if tag is None or v[3] == tag]:
+            del plans[key]
 
     def _take_backward_plan(self, slot_ids, offsets, psw, mode, nbytes):
         plans = getattr(self, "_bwd_plans", None)
@@ -295,13 +306,14 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         entry = plans.pop((slot_ids.data_ptr(), slot_ids.numel()), None)
         if entry is None:
             return None
-        ws, off_ptr, planned_bytes = entry
-        if planned_bytes != nbytes:
+        ws, off_ptr, planned_bytes = entry[:3]
+        if planned_bytes != nbytes or off_ptr != offsets.data_ptr():
             return None
         return ws
 
     # ---- forward --------------------------------------------------------------------------------------------------------------
     def _embed(self, slot_ids, offsets, per_sample_weights, layout="bag_major", layout_batch=0):
+        self.cache_weight_mgr.wait_rows()       # rows that a prepare_ids left moving on a copy stream
         return embedding_bag_cached(self.cache_weight_mgr.cuda_cached_weight, slot_ids, offsets, per_sample_weights,
                                     self.include_last_offset, self.mode, self.padding_idx, layout, layout_batch, self)
 
@@ -330,7 +342,10 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         self.cache_op = cache_op
 
     def set_cache_mgr_async_copy(self, flag):
-        self.cache_weight_mgr._async_copy = flag
+        """Reference flag --use_cache_mgr_async_copy (recsys/dlrm_main.py:121,354): the PCIe row traffic of
+        prepare_ids runs on the manager's copy stream; forward waits (on the device) for the missed rows only, the
+        write-back of the victims proceeds under the following steps."""
+        self.cache_weight_mgr._async_copy = bool(flag)
 
     def element_size(self):
         return self.weight.element_size()

@@ -1,21 +1,28 @@
 // The cache manager on the device: CachedParamMgr.prepare_ids / _prepare_rows_on_cuda / flush / reorder's preload
 // (reference call site recsys/dlrm_main.py:259).
 //
-// The reference finds the unique rows of a window with sort-based unique/isin/topk over millions of ids and moves
-// rows with CPU gather/scatter + staged memcpys.  Here:
-//   * probe       : one pass over the ids.  Resident rows answer from the dense int32 row->slot map and stamp their
-//                   slot with the window epoch (that stamp IS the evict backlist); missing rows set a bit in a per-row
+// The reference finds the unique rows of a window with sort-based unique/isin/topk over millions of ids, moves rows
+// with CPU gather/scatter + staged memcpys and synchronises the device 8+ times per call.  Here one call ENQUEUES a
+// fixed sequence of kernels and never waits for the GPU: every count (misses M, evictions E, free slots) stays in
+// device memory, grids are upper bounds, and the state-changing kernels are gated by a device-side verdict.
+//   * probe       : one pass over the ids.  Resident rows answer from the dense int32 row->slot map and set their
+//                   slot's bit in a hit bitmap (first setter counts the unique hit); missing rows set a bit in a per-row
 //                   bitmap and append their position to a fix-up list.  No sort.
-//   * rank        : popcount-scan of the bitmap emits the missed rows in ascending row order (the reference's
+//   * rank        : popcount-scan of the row bitmap emits the missed rows in ascending row order (the reference's
 //                   sorted-unique contract) and their count M.
-//   * victims     : radix-select of the E = M - free smallest (freq, slot) [LFU] / largest row [DATASET] keys among
-//                   slots not stamped by this window; ties broken by ascending slot.
-//   * swap        : i-th smallest missed row -> i-th lowest free slot.  One kernel moves both directions: the evicted
-//                   row is stored straight into the pinned host table and the missed row is loaded straight from it
-//                   (zero-copy over PCIe, 128-bit accesses), so both PCIe directions run concurrently and no CPU
-//                   thread touches a row.
+//   * decide      : one thread applies the A.3 capacity assert and the id-range check, fixes E = max(0, M - free).
+//   * victims     : radix-select of the E smallest (freq, slot) [LFU] / largest row [DATASET] keys among slots that are
+//                   neither hit by this call nor stamped by a protected window; ties by ascending slot.
+//   * commit      : i-th smallest missed row -> i-th lowest free slot; maps, LFU counters, window stamps.
+//   * row traffic : victims are ranked by HOST ROW through the same bitmap machinery -- a zero-copy scatter over PCIe
+//                   runs at 48.8 GB/s when its destinations ascend and at 33.7 GB/s when they do not
+//                   (scripts/probes/host_scatter_probe.cu) -- parked in an HBM staging buffer when a copy stream is
+//                   used, the missed rows are gathered from the pinned host table (128-bit zero-copy loads, ascending
+//                   rows), and the parked victims are then written back.  Reads and writes are separate kernels and
+//                   never overlap: SM-issued PCIe reads and writes share one request queue (16 + 16 GB/s together).
 //   * fix-up      : ids that missed get their new slot; LFU counters += multiplicity.
 // Integer / byte work throughout; HBM- (maps) and PCIe- (rows) bound.
+#include <string.h>
 #include "common.cuh"
 #include "scan.cuh"
 #include "profile.cuh"
@@ -26,9 +33,15 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// counters read back by the host (int32 each)
+// per-call counters in the workspace (int32 each)
 enum : int { kCtrUniqueHits = 0, kCtrMissLookups = 1, kCtrBadIndex = 2, kCtrUniqueMisses = 3, kCtrFlushed = 4,
              kCtrEvictable = 5,
+             kCtrEvict = 6,      // E of this call (0 when the call is rejected)
+             kCtrStatus = 7,     // device-side verdict: CEBAG_OK / CEBAG_ERR_CAPACITY / CEBAG_ERR_INDEX
+             kCtrEpoch = 8,      // window stamp of this call = dev_state[EPOCH] + 1
+             kCtrAdmit = 9,      // M of this call (0 when rejected)
+             kCtrVictims = 10,   // victims ranked by row (== E)
+             kCtrFixups = 11,    // positions to fix up (0 when rejected)
              kNumCounters = 16 };
 
 struct SelectState {             // radix-select of the k smallest keys
@@ -39,6 +52,73 @@ struct SelectState {             // radix-select of the k smallest keys
 
 __device__ __forceinline__ int32_t row_of_id(const cebag_table& t, int64_t id) {
     return t.idx_map ? __ldg(t.idx_map + id) : (int32_t)id;
+}
+
+// ---- call bracket -------------------------------------------------------------------------------------------------
+__global__ void begin_call_kernel(const cebag_table t, int32_t* __restrict__ counters) {
+    if (threadIdx.x < kNumCounters) counters[threadIdx.x] = 0;
+    __syncwarp();
+    if (threadIdx.x == 0) counters[kCtrEpoch] = (int32_t)t.dev_state[CEBAG_STATE_EPOCH] + 1;
+}
+
+// The verdict of the call (A.3 assert, id range) and E, from the device-resident counts.  One CTA of 256 threads:
+// thread 0 decides, everybody clears the radix-select histogram.
+__global__ void __launch_bounds__(256)
+decide_kernel(const cebag_table t, int32_t* __restrict__ counters, SelectState* __restrict__ sel) {
+    sel->hist[threadIdx.x] = 0;
+    if (threadIdx.x != 0) return;
+    const long long M = counters[kCtrUniqueMisses], H = counters[kCtrUniqueHits];
+    const long long avail = t.dev_state[CEBAG_STATE_AVAIL];
+    int status = CEBAG_OK;
+    long long E = 0;
+    if (counters[kCtrBadIndex]) status = CEBAG_ERR_INDEX;
+    else if (H + M > (long long)t.cache_rows) status = CEBAG_ERR_CAPACITY;
+    else {
+        E = M > avail ? M - avail : 0;
+        // rows of an earlier, still protected window cannot be victims: enough others must exist
+        if (t.protect_windows > 1 && E > (long long)counters[kCtrEvictable]) status = CEBAG_ERR_CAPACITY;
+    }
+    const bool ok = status == CEBAG_OK;
+    counters[kCtrStatus] = status;
+    counters[kCtrEvict] = ok ? (int32_t)E : 0;
+    counters[kCtrAdmit] = ok ? (int32_t)M : 0;
+    counters[kCtrFixups] = ok ? counters[kCtrMissLookups] : 0;
+    sel->prefix = 0ull;
+    sel->k = ok ? E : 0;
+}
+
+// Last kernel of the map work: the device-resident table state moves on (only if the call was accepted) and the
+// result record goes to pinned host memory, status last.
+__global__ void end_call_kernel(const cebag_table t, const int32_t* __restrict__ counters, int64_t n,
+                                cebag_prepare_result* __restrict__ result) {
+    if (threadIdx.x != 0) return;
+    const int status = counters[kCtrStatus];
+    const long long M = counters[kCtrAdmit], E = counters[kCtrEvict];
+    if (status == CEBAG_OK) {
+        t.dev_state[CEBAG_STATE_AVAIL] += E - M;
+        t.dev_state[CEBAG_STATE_EPOCH] = counters[kCtrEpoch];
+    }
+    t.dev_state[CEBAG_STATE_CALLS] += 1;
+    if (result) {
+        result->unique_hits = counters[kCtrUniqueHits];
+        result->unique_misses = counters[kCtrUniqueMisses];
+        result->evicted = E;
+        result->miss_lookups = counters[kCtrMissLookups];
+        result->total_lookups = n;
+        result->evictable = counters[kCtrEvictable];
+        result->avail_after = t.dev_state[CEBAG_STATE_AVAIL];
+        __threadfence_system();
+        *reinterpret_cast<volatile int64_t*>(&result->status) = status;
+        __threadfence_system();
+    }
+}
+
+// a rejected call must leave the miss bitmap all-zero again (an accepted one clears its bits as it commits)
+__global__ void __launch_bounds__(kThreads)
+clear_bitmap_if_rejected_kernel(const cebag_table t, const int32_t* __restrict__ counters, int64_t words) {
+    if (counters[kCtrStatus] == CEBAG_OK) return;
+    for (int64_t w = (int64_t)blockIdx.x * kThreads + threadIdx.x; w < words; w += (int64_t)gridDim.x * kThreads)
+        t.miss_bitmap[w] = 0u;
 }
 
 // ---- probe ---------------------------------------------------------------------------------------------------------
@@ -75,10 +155,10 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
             bool miss = live[u] && slot[u] < 0;
             if (live[u] && !miss) {
                 out[i] = slot[u];
-                if (t.slot_epoch[slot[u]] != t.epoch) {
-                    int32_t old = atomicExch(&t.slot_epoch[slot[u]], t.epoch);
-                    uniq += (old != t.epoch);
-                }
+                // the slot is needed by this call: the first id to say so counts the unique hit
+                const uint32_t bit = 1u << (slot[u] & 31);
+                uint32_t* word = t.hit_bitmap + (slot[u] >> 5);
+                if (!(*reinterpret_cast<volatile uint32_t*>(word) & bit)) uniq += !(atomicOr(word, bit) & bit);
             }
             // warp-aggregated append of the positions that missed
             unsigned m = __ballot_sync(0xffffffffu, miss);
@@ -101,13 +181,20 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
     if (lane == 0 && uniq) atomicAdd(&counters[kCtrUniqueHits], uniq);
 }
 
-// ---- bitmap ranking: missed rows in ascending order -----------------------------------------------------------------
+// ---- bitmap ranking: rows in ascending order -----------------------------------------------------------------------
+// Used twice per call: for the missed rows (gate = the count of ids that missed) and, after the commit, for the
+// victims' host rows (gate = E).  A zero gate means an empty bitmap: nothing is read.
 constexpr int kWordsPerThread = 16;
 constexpr int kWordsPerBlock = kScanThreads * kWordsPerThread;   // 4096 words = 131072 rows per CTA
 
 __global__ void __launch_bounds__(kScanThreads)
-bitmap_count_kernel(const uint32_t* __restrict__ bitmap, int64_t words, int32_t* __restrict__ block_sums) {
+bitmap_count_kernel(const uint32_t* __restrict__ bitmap, int64_t words, int32_t* __restrict__ block_sums,
+                    const int32_t* __restrict__ gate) {
     __shared__ int32_t warp_sums[32];
+    if (*gate == 0) {
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = 0;
+        return;
+    }
     int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
     int32_t c = 0;
 #pragma unroll
@@ -118,8 +205,9 @@ bitmap_count_kernel(const uint32_t* __restrict__ bitmap, int64_t words, int32_t*
 
 __global__ void __launch_bounds__(kScanThreads)
 bitmap_emit_kernel(const uint32_t* __restrict__ bitmap, int64_t words, const int32_t* __restrict__ block_base,
-                   int32_t* __restrict__ rows_out, int64_t capacity) {
+                   int32_t* __restrict__ rows_out, int64_t capacity, const int32_t* __restrict__ gate) {
     __shared__ int32_t warp_sums[32];
+    if (*gate == 0) return;
     int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
     uint32_t w[kWordsPerThread];
     int32_t c = 0;
@@ -143,23 +231,28 @@ bitmap_emit_kernel(const uint32_t* __restrict__ bitmap, int64_t words, const int
 }
 
 // ---- victim selection ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, unsigned long long* key) {
+// key of slot s if it may be evicted by the call stamped `epoch`: occupied, not hit by this call, not stamped by a
+// protected window
+__device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, int32_t epoch, unsigned long long* key) {
     int32_t row = t.slot2row[s];
-    if (row < 0) return false;                                       // empty
+    if (row < 0) return false;                                                  // empty
+    if ((t.hit_bitmap[s >> 5] >> (s & 31)) & 1u) return false;                   // needed by this call
     const int32_t stamp = t.slot_epoch[s];
-    if (stamp != 0 && t.epoch - stamp < t.protect_windows) return false;   // needed by a protected window
-    if (t.strategy == CEBAG_EVICT_LFU) *key = (unsigned long long)t.freq[s];   // smallest counter first
-    else *key = (unsigned long long)(0xffffffffu - (uint32_t)row);             // largest row first
+    if (stamp != 0 && epoch - stamp < t.protect_windows) return false;          // needed by a protected window
+    if (t.strategy == CEBAG_EVICT_LFU) *key = (unsigned long long)t.freq[s];    // smallest counter first
+    else *key = (unsigned long long)(0xffffffffu - (uint32_t)row);              // largest row first
     return true;
 }
 
 // how many occupied slots may be evicted (only needed when more than the current window is protected)
 __global__ void __launch_bounds__(kThreads)
 count_evictable_kernel(const cebag_table t, int32_t* __restrict__ counters) {
+    if (counters[kCtrMissLookups] == 0) return;
+    const int32_t epoch = counters[kCtrEpoch];
     int32_t c = 0;
     for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < t.cache_rows; s += (int64_t)gridDim.x * kThreads) {
         unsigned long long key;
-        c += slot_key(t, s, &key) ? 1 : 0;
+        c += slot_key(t, s, epoch, &key) ? 1 : 0;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
@@ -167,14 +260,17 @@ count_evictable_kernel(const cebag_table t, int32_t* __restrict__ counters) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-select_hist_kernel(const cebag_table t, SelectState* __restrict__ st, int shift, int first_pass) {
+select_hist_kernel(const cebag_table t, const int32_t* __restrict__ counters, SelectState* __restrict__ st, int shift,
+                   int first_pass) {
     __shared__ int h[256];
+    if (counters[kCtrEvict] == 0) return;
+    const int32_t epoch = counters[kCtrEpoch];
     h[threadIdx.x] = 0;
     __syncthreads();
     const unsigned long long prefix = st->prefix;
     for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < t.cache_rows; s += (int64_t)gridDim.x * kThreads) {
         unsigned long long key;
-        if (!slot_key(t, s, &key)) continue;
+        if (!slot_key(t, s, epoch, &key)) continue;
         if (!first_pass && (key >> (shift + 8)) != (prefix >> (shift + 8))) continue;
         atomicAdd(&h[(key >> shift) & 255u], 1);
     }
@@ -182,9 +278,11 @@ select_hist_kernel(const cebag_table t, SelectState* __restrict__ st, int shift,
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(256) select_choose_kernel(SelectState* __restrict__ st, int shift) {
+__global__ void __launch_bounds__(256)
+select_choose_kernel(const int32_t* __restrict__ counters, SelectState* __restrict__ st, int shift) {
     // 256 threads, one per bin: the digit whose cumulative count first reaches k
     __shared__ int32_t warp_sums[32];
+    if (counters[kCtrEvict] == 0) return;
     const long long k = st->k;
     const int32_t c = st->hist[threadIdx.x];
     const int32_t excl = block_exclusive_scan<256>(c, warp_sums);
@@ -198,18 +296,24 @@ __global__ void __launch_bounds__(256) select_choose_kernel(SelectState* __restr
 
 // eq[s] = 1 where an eligible slot's key equals the threshold (LFU ties)
 __global__ void __launch_bounds__(kThreads)
-select_equal_flags_kernel(const cebag_table t, const SelectState* __restrict__ st, int32_t* __restrict__ eq) {
+select_equal_flags_kernel(const cebag_table t, const int32_t* __restrict__ counters, const SelectState* __restrict__ st,
+                          int32_t* __restrict__ eq) {
+    if (counters[kCtrEvict] == 0) return;
+    const int32_t epoch = counters[kCtrEpoch];
     const unsigned long long thr = st->prefix;
     for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < t.cache_rows; s += (int64_t)gridDim.x * kThreads) {
         unsigned long long key;
-        eq[s] = (slot_key(t, s, &key) && key == thr) ? 1 : 0;
+        eq[s] = (slot_key(t, s, epoch, &key) && key == thr) ? 1 : 0;
     }
 }
 
 // free[s] = 1 for empty slots and for this call's victims
 __global__ void __launch_bounds__(kThreads)
-free_flags_kernel(const cebag_table t, const SelectState* __restrict__ st, const int32_t* __restrict__ eq_rank,
-                  int evicting, int32_t* __restrict__ free_flag) {
+free_flags_kernel(const cebag_table t, const int32_t* __restrict__ counters, const SelectState* __restrict__ st,
+                  const int32_t* __restrict__ eq_rank, int32_t* __restrict__ free_flag) {
+    if (counters[kCtrAdmit] == 0) return;
+    const bool evicting = counters[kCtrEvict] > 0;
+    const int32_t epoch = counters[kCtrEpoch];
     unsigned long long thr = 0;
     long long take = 0;
     if (evicting) { thr = st->prefix; take = st->k; }
@@ -217,7 +321,7 @@ free_flags_kernel(const cebag_table t, const SelectState* __restrict__ st, const
         int f = t.slot2row[s] < 0;
         if (!f && evicting) {
             unsigned long long key;
-            if (slot_key(t, s, &key)) {
+            if (slot_key(t, s, epoch, &key)) {
                 if (key < thr) f = 1;
                 else if (key == thr) f = eq_rank ? (eq_rank[s] < take) : 1;
             }
@@ -227,10 +331,80 @@ free_flags_kernel(const cebag_table t, const SelectState* __restrict__ st, const
 }
 
 __global__ void __launch_bounds__(kThreads)
-emit_free_slots_kernel(const int32_t* __restrict__ free_flag_in, const int32_t* __restrict__ free_pos, int64_t cache_rows,
-                       int32_t* __restrict__ free_slots, int64_t want) {
+emit_free_slots_kernel(const int32_t* __restrict__ counters, const int32_t* __restrict__ free_flag_in,
+                       const int32_t* __restrict__ free_pos, int64_t cache_rows, int32_t* __restrict__ free_slots) {
+    const int32_t want = counters[kCtrAdmit];
+    if (want == 0) return;
     for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < cache_rows; s += (int64_t)gridDim.x * kThreads) {
         if (free_flag_in[s] && free_pos[s] < want) free_slots[free_pos[s]] = (int32_t)s;
+    }
+}
+
+// ---- commit ----------------------------------------------------------------------------------------------------------------
+// Admission, maps: the j-th smallest missed row goes to the j-th lowest free slot (A.4 steps 4-6).  Records the row the
+// slot held (the victim, or -1), updates both maps, the LFU counter, the window stamp and the miss bitmap.  The
+// victim's row2slot entry becomes the marker -2 - slot ("not resident; its last value is still in that slot") until
+// resolve_victims has ranked the victims by host row.
+__global__ void __launch_bounds__(kThreads)
+commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ counters,
+                        const int32_t* __restrict__ miss_rows, const int32_t* __restrict__ free_slots,
+                        int32_t* __restrict__ victim_rows) {
+    const int64_t m = counters[kCtrAdmit];
+    const int32_t epoch = counters[kCtrEpoch];
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kThreads) {
+        const int32_t row = miss_rows[j];
+        const int32_t slot = free_slots[j];
+        const int32_t old_row = t.slot2row[slot];
+        victim_rows[j] = old_row;
+        if (old_row >= 0) t.row2slot[old_row] = -2 - slot;
+        t.slot2row[slot] = row;
+        t.row2slot[row] = slot;
+        t.slot_epoch[slot] = epoch;
+        if (t.freq) t.freq[slot] = 0;
+        t.miss_bitmap[row >> 5] = 0u;   // every row of this word was missed in this call and is being admitted
+    }
+}
+
+// slots hit by this call get the window stamp (only if the call was accepted); the hit bitmap is all-zero again
+__global__ void __launch_bounds__(kThreads)
+stamp_hits_kernel(const cebag_table t, const int32_t* __restrict__ counters, int64_t words) {
+    const bool ok = counters[kCtrStatus] == CEBAG_OK;
+    const int32_t epoch = counters[kCtrEpoch];
+    for (int64_t w = (int64_t)blockIdx.x * kThreads + threadIdx.x; w < words; w += (int64_t)gridDim.x * kThreads) {
+        uint32_t bits = t.hit_bitmap[w];
+        if (!bits) continue;
+        t.hit_bitmap[w] = 0u;
+        if (!ok) continue;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            t.slot_epoch[w * 32 + b] = epoch;
+        }
+    }
+}
+
+// the victims' host rows go into the (all-zero again) row bitmap; ranking it gives them in ascending row order
+__global__ void __launch_bounds__(kThreads)
+mark_victims_kernel(const cebag_table t, const int32_t* __restrict__ counters, const int32_t* __restrict__ victim_rows) {
+    if (counters[kCtrEvict] == 0) return;
+    const int64_t m = counters[kCtrAdmit];
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kThreads) {
+        const int32_t old_row = victim_rows[j];
+        if (old_row >= 0) atomicOr(t.miss_bitmap + (old_row >> 5), 1u << (old_row & 31));
+    }
+}
+
+// i-th victim by host row: which slot still holds its last value?  Takes the marker out of row2slot and the bit out
+// of the bitmap.
+__global__ void __launch_bounds__(kThreads)
+resolve_victims_kernel(const cebag_table t, const int32_t* __restrict__ counters,
+                       const int32_t* __restrict__ victims_sorted, int32_t* __restrict__ victim_slots) {
+    const int64_t e = counters[kCtrEvict];
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < e; i += (int64_t)gridDim.x * kThreads) {
+        const int32_t row = victims_sorted[i];
+        victim_slots[i] = -2 - t.row2slot[row];
+        t.row2slot[row] = -1;
+        t.miss_bitmap[row >> 5] = 0u;   // every bit of this word is a victim of this call
     }
 }
 
@@ -247,51 +421,55 @@ __device__ __forceinline__ void warp_copy_row(float* __restrict__ dst, const flo
     }
 }
 
-// Admission, step 1 (maps): the j-th smallest missed row goes to the j-th lowest free slot (A.4 steps 4-6).  Records
-// the row the slot held (the victim, or -1) for the copy kernels and updates both maps, the LFU counter, the window
-// stamp and the miss bitmap.  Everything after this kernel that only needs the maps (fix-up of the missed positions,
-// LFU counts, backward plans) can proceed while the rows are still moving.
-__global__ void __launch_bounds__(kThreads)
-commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ miss_rows,
-                        const int32_t* __restrict__ free_slots, int32_t* __restrict__ victim_rows, int64_t m) {
-    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kThreads) {
-        const int32_t row = miss_rows[j];
-        const int32_t slot = free_slots[j];
-        const int32_t old_row = t.slot2row[slot];
-        victim_rows[j] = old_row;
-        if (old_row >= 0) t.row2slot[old_row] = -1;
-        t.slot2row[slot] = row;
-        t.row2slot[row] = slot;
-        t.slot_epoch[slot] = t.epoch;
-        if (t.freq) t.freq[slot] = 0;
-        t.miss_bitmap[row >> 5] = 0u;   // every row of this word was missed in this call and is being admitted
-    }
-}
+// Row traffic of one call, one warp per row.  All lists are in ascending HOST ROW order.
+//   kParkVictims : cache[victim_slots[i]] -> stage[i]                       i in [0, min(E, stage_rows))    HBM -> HBM
+//   kWriteDirect : cache[victim_slots[i]] -> host_table[victims_sorted[i]]  i in [first, E)                 D2H
+//   kWriteParked : stage[i]               -> host_table[victims_sorted[i]]  i in [0, min(E, stage_rows))    D2H
+//   kFill        : host_table[miss_rows[j]] -> cache[free_slots[j]]         j in [0, M)                     H2D
+// The row-wise Adagrad state travels with the row.
+enum : int { kParkVictims = 0, kWriteDirect = 1, kWriteParked = 2, kFill = 3 };
 
-// Admission, step 2 (rows), one warp per row with zero-copy 128-bit accesses to the pinned host table.
-// direction 1: victims HBM -> host table (write-back), direction 0: missed rows host table -> HBM (fill).
-// The two directions are separate launches: interleaving posted writes and reads from one kernel halves the PCIe
-// throughput of both (measured: 20-24 GB/s each way fused vs 51 GB/s for a pure gather; PCIe reads may not pass writes).
-template <bool VEC>
+struct RowLists {
+    const int32_t* miss_rows;
+    const int32_t* free_slots;
+    const int32_t* victims_sorted;
+    const int32_t* victim_slots;
+    float* stage;
+    float* stage_state;
+    int64_t stage_rows;
+};
+
+template <bool VEC, int WHAT>
 __global__ void __launch_bounds__(kThreads)
-copy_rows_kernel(const cebag_table t, const int32_t* __restrict__ miss_rows, const int32_t* __restrict__ free_slots,
-                 const int32_t* __restrict__ victim_rows, int64_t m, int direction) {
+move_window_rows_kernel(const cebag_table t, const int32_t* __restrict__ counters, const RowLists L) {
     const int lane = lane_id();
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t num_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int dim = t.dim;
-    for (int64_t j = warp; j < m; j += num_warps) {
-        const int32_t slot = free_slots[j];
-        float* crow = t.cache + (int64_t)slot * dim;
-        if (direction == 1) {
-            const int32_t old_row = victim_rows[j];
-            if (old_row < 0) continue;
-            warp_copy_row<VEC>(t.host_table + (int64_t)old_row * dim, crow, dim, lane);
-            if (lane == 0 && t.host_state && t.cache_state) t.host_state[old_row] = t.cache_state[slot];
+    const bool with_state = t.host_state && t.cache_state;
+    const int64_t e = counters[kCtrEvict];
+    const int64_t parked = L.stage ? (e < L.stage_rows ? e : L.stage_rows) : 0;
+    int64_t lo = 0, hi = 0;
+    if (WHAT == kParkVictims || WHAT == kWriteParked) hi = parked;
+    else if (WHAT == kWriteDirect) { lo = parked; hi = e; }
+    else hi = counters[kCtrAdmit];
+    for (int64_t j = lo + warp; j < hi; j += num_warps) {
+        if (WHAT == kFill) {
+            const int32_t slot = L.free_slots[j], row = L.miss_rows[j];
+            warp_copy_row<VEC>(t.cache + (int64_t)slot * dim, t.host_table + (int64_t)row * dim, dim, lane);
+            if (lane == 0 && with_state) t.cache_state[slot] = t.host_state[row];
+        } else if (WHAT == kParkVictims) {
+            const int32_t slot = L.victim_slots[j];
+            warp_copy_row<VEC>(L.stage + j * dim, t.cache + (int64_t)slot * dim, dim, lane);
+            if (lane == 0 && with_state && L.stage_state) L.stage_state[j] = t.cache_state[slot];
+        } else if (WHAT == kWriteDirect) {
+            const int32_t slot = L.victim_slots[j], row = L.victims_sorted[j];
+            warp_copy_row<VEC>(t.host_table + (int64_t)row * dim, t.cache + (int64_t)slot * dim, dim, lane);
+            if (lane == 0 && with_state) t.host_state[row] = t.cache_state[slot];
         } else {
-            const int32_t row = miss_rows[j];
-            warp_copy_row<VEC>(crow, t.host_table + (int64_t)row * dim, dim, lane);
-            if (lane == 0 && t.host_state && t.cache_state) t.cache_state[slot] = t.host_state[row];
+            const int32_t row = L.victims_sorted[j];
+            warp_copy_row<VEC>(t.host_table + (int64_t)row * dim, L.stage + j * dim, dim, lane);
+            if (lane == 0 && with_state && L.stage_state) t.host_state[row] = L.stage_state[j];
         }
     }
 }
@@ -328,6 +506,10 @@ move_rows_kernel(const cebag_table t, const int32_t* __restrict__ rows, const in
     }
 }
 
+__global__ void add_avail_kernel(const cebag_table t, long long delta) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) t.dev_state[CEBAG_STATE_AVAIL] += delta;
+}
+
 // flush: every resident row goes back to the host table, maps are emptied
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -353,12 +535,17 @@ flush_kernel(const cebag_table t, int32_t* __restrict__ counters) {
         }
     }
     if (lane == 0 && moved) atomicAdd(&counters[kCtrFlushed], moved);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        t.dev_state[CEBAG_STATE_AVAIL] = t.cache_rows;
+        t.dev_state[CEBAG_STATE_EPOCH] = 0;
+    }
 }
 
 // ---- fix-up and LFU count ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-fixup_kernel(const cebag_table t, const int64_t* __restrict__ ids, const int32_t* __restrict__ miss_pos, int64_t count,
-             int64_t* __restrict__ out) {
+fixup_kernel(const cebag_table t, const int32_t* __restrict__ counters, const int64_t* __restrict__ ids,
+             const int32_t* __restrict__ miss_pos, int64_t* __restrict__ out) {
+    const int64_t count = counters[kCtrFixups];
     for (int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x; k < count; k += (int64_t)gridDim.x * kThreads) {
         int32_t i = miss_pos[k];
         out[i] = t.row2slot[row_of_id(t, ids[i])];
@@ -373,9 +560,10 @@ constexpr int kLfuTile = 2048;            // ids per CTA iteration
 constexpr int kLfuTable = 4096;           // hash entries (load factor <= 0.5)
 
 __global__ void __launch_bounds__(kThreads)
-lfu_count_kernel(const cebag_table t, const int64_t* __restrict__ slots, int64_t n) {
+lfu_count_kernel(const cebag_table t, const int32_t* __restrict__ counters, const int64_t* __restrict__ slots, int64_t n) {
     __shared__ int s_key[kLfuTable];
     __shared__ int s_cnt[kLfuTable];
+    if (counters[kCtrStatus] != CEBAG_OK) return;
     const int lane = lane_id();
     for (int64_t base = (int64_t)blockIdx.x * kLfuTile; base < n; base += (int64_t)gridDim.x * kLfuTile) {
         for (int e = threadIdx.x; e < kLfuTable; e += kThreads) { s_key[e] = -1; s_cnt[e] = 0; }
@@ -408,7 +596,7 @@ lfu_count_kernel(const cebag_table t, const int64_t* __restrict__ slots, int64_t
 
 struct PrepLayout {
     size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, total;
-    int64_t bitmap_blocks, words;
+    int64_t bitmap_blocks, words, hit_words;
 };
 
 PrepLayout prep_layout(const cebag_table* t, int64_t n) {
@@ -417,6 +605,7 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     int64_t nn = n > 0 ? n : 1;
     int64_t C = t->cache_rows;
     L.words = ceil_div(t->num_rows, 32);
+    L.hit_words = ceil_div(C, 32);
     L.bitmap_blocks = ceil_div(L.words, kWordsPerBlock);
     size_t off = 0;
     L.counters = off; off += align(kNumCounters * 4);
@@ -425,19 +614,13 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     L.miss_rows = off; off += align((size_t)C * 4);
     L.free_slots = off; off += align((size_t)C * 4);
     L.victim_rows = off; off += align((size_t)C * 4);
-    L.flags_a = off; off += align((size_t)C * 4);
-    L.flags_b = off; off += align((size_t)C * 4);
+    L.flags_a = off; off += align((size_t)C * 4);      // free flags, later: the victims in ascending row order
+    L.flags_b = off; off += align((size_t)C * 4);      // tie ranks / free positions, later: the victims' slots
     L.bitmap_sums = off; off += align((size_t)(L.bitmap_blocks + 1) * 4);
     int64_t longest = C > L.bitmap_blocks ? C : L.bitmap_blocks;
     L.scan_ws = off; off += align(scan_workspace_bytes(longest));
     L.total = off;
     return L;
-}
-
-int read_counters(const int32_t* dev, int32_t* pinned, cudaStream_t stream) {
-    CEBAG_CUDA_CHECK(cudaMemcpyAsync(pinned, dev, kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
-    CEBAG_CUDA_CHECK(cudaStreamSynchronize(stream));
-    return CEBAG_OK;
 }
 
 bool table_vec_ok(const cebag_table* t) {
@@ -449,14 +632,21 @@ int check_table(const cebag_table* t) {
     CEBAG_REQUIRE(t->num_rows > 0 && t->num_rows < ((int64_t)1 << 31), "num_rows must be in (0, 2^31)");
     CEBAG_REQUIRE(t->dim > 0 && t->cache_rows > 0, "dim / cache_rows");
     CEBAG_REQUIRE(t->strategy == CEBAG_EVICT_LFU || t->strategy == CEBAG_EVICT_DATASET, "strategy");
-    CEBAG_REQUIRE(t->host_table && t->cache && t->row2slot && t->slot2row && t->slot_epoch && t->miss_bitmap,
-                  "table pointers");
+    CEBAG_REQUIRE(t->host_table && t->cache && t->row2slot && t->slot2row && t->slot_epoch && t->miss_bitmap &&
+                  t->hit_bitmap && t->dev_state, "table pointers");
     CEBAG_REQUIRE(t->strategy != CEBAG_EVICT_LFU || t->freq != nullptr, "LFU needs freq");
     CEBAG_REQUIRE(t->protect_windows >= 1 && t->protect_windows <= 1024, "protect_windows");
     return CEBAG_OK;
 }
 
-// single-row helpers take their (row, slot) by value: stage them in a tiny device buffer owned by the stream order
+int read_state(const cebag_table* t, int64_t* state, cudaStream_t stream) {
+    CEBAG_CUDA_CHECK(cudaMemcpyAsync(state, t->dev_state, CEBAG_STATE_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                     stream));
+    CEBAG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return CEBAG_OK;
+}
+
+// single-row helpers take their (row, slot) by value
 __global__ void move_one_kernel(const cebag_table t, int32_t row, int32_t slot, int direction, int vec) {
     const int lane = lane_id();
     int32_t r = direction == 0 ? row : t.slot2row[slot];
@@ -470,12 +660,25 @@ __global__ void move_one_kernel(const cebag_table t, int32_t row, int32_t slot, 
             if (t.host_state && t.cache_state) t.cache_state[slot] = t.host_state[r];
             t.slot2row[slot] = r; t.row2slot[r] = slot;
             if (t.freq) t.freq[slot] = 0;
+            t.dev_state[CEBAG_STATE_AVAIL] -= 1;
         } else {
             if (t.host_state && t.cache_state) t.host_state[r] = t.cache_state[slot];
             t.slot2row[slot] = -1; t.row2slot[r] = -1;
             if (t.freq) t.freq[slot] = CEBAG_FREQ_EMPTY;
+            t.dev_state[CEBAG_STATE_AVAIL] += 1;
         }
     }
+}
+
+template <int WHAT>
+int launch_rows(const cebag_table* t, const int32_t* counters, const RowLists& lists, int grid, int threads,
+                cudaStream_t stream) {
+    if (table_vec_ok(t) && (WHAT == kFill || WHAT == kWriteDirect || aligned16(lists.stage)))
+        move_window_rows_kernel<true, WHAT><<<grid, threads, 0, stream>>>(*t, counters, lists);
+    else
+        move_window_rows_kernel<false, WHAT><<<grid, threads, 0, stream>>>(*t, counters, lists);
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
 }
 
 }  // namespace
@@ -488,19 +691,30 @@ extern "C" size_t cebag_prepare_workspace_bytes(const cebag_table* t, int64_t n_
     return prep_layout(t, n_ids).total;
 }
 
-extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
-                                 const cebag_workspace* ws, cebag_prepare_stats* stats, void* stream_) {
+extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
+                                       const cebag_workspace* ws, cebag_prepare_result* result, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_table(t);
     if (rc) return rc;
-    CEBAG_REQUIRE(ws && ws->device && ws->pinned && stats, "workspace / stats");
+    CEBAG_REQUIRE(ws && ws->device && result, "workspace / result");
     CEBAG_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "n");
-    stats->unique_hits = stats->unique_misses = stats->evicted = stats->miss_lookups = 0;
-    stats->total_lookups = n;
-    if (n == 0) return CEBAG_OK;
+    memset(result, 0, sizeof(*result));
+    result->total_lookups = n;
+    if (n == 0) {
+        if (ws->copy_stream && ws->copy_done_event)
+            CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->copy_done_event),
+                                             reinterpret_cast<cudaStream_t>(ws->copy_stream)));
+        if (ws->copy_stream && ws->writeback_done_event)
+            CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->writeback_done_event),
+                                             reinterpret_cast<cudaStream_t>(ws->copy_stream)));
+        return CEBAG_OK;
+    }
     CEBAG_REQUIRE(ids && slot_ids_out, "ids / out");
     PrepLayout L = prep_layout(t, n);
     CEBAG_REQUIRE(ws->device_bytes >= L.total, "prepare workspace too small");
+    cebag_prepare_result* result_dev = nullptr;
+    CEBAG_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&result_dev), result, 0));
+    result->status = CEBAG_PREPARE_PENDING;
     char* base = reinterpret_cast<char*>(ws->device);
     int32_t* counters = reinterpret_cast<int32_t*>(base + L.counters);
     SelectState* sel = reinterpret_cast<SelectState*>(base + L.select);
@@ -512,165 +726,200 @@ extern "C" int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, 
     int32_t* flags_b = reinterpret_cast<int32_t*>(base + L.flags_b);
     int32_t* bitmap_sums = reinterpret_cast<int32_t*>(base + L.bitmap_sums);
     int32_t* scan_ws = reinterpret_cast<int32_t*>(base + L.scan_ws);
-    int32_t* host_ctr = reinterpret_cast<int32_t*>(ws->pinned);
     const int64_t C = t->cache_rows;
+    const int64_t admit_bound = n < C ? n : C;          // M <= min(n, C) whenever the call is accepted
+    const int sgrid = grid_for(C, kThreads, 8);
+    const bool lfu = t->strategy == CEBAG_EVICT_LFU;
 
-    // a new window: stamps of earlier windows stop protecting their slots
-    t->epoch = t->epoch >= 0x7ffffff0 ? 1 : t->epoch + 1;
-    if (t->epoch == 1) CEBAG_CUDA_CHECK(cudaMemsetAsync(t->slot_epoch, 0, (size_t)C * 4, stream));
-
-    CEBAG_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * 4, stream));
     {
-        KernelScope scope(kKernProbe, stream);
+        KernelScope scope(kKernProbe, stream, 2);
+        begin_call_kernel<<<1, 32, 0, stream>>>(*t, counters);
         probe_kernel<<<grid_for(ceil_div(n, kProbeIds), kThreads, 8), kThreads, 0, stream>>>(*t, ids, n, slot_ids_out,
                                                                                             miss_pos, counters);
+        CEBAG_LAUNCH_CHECK();
     }
-    CEBAG_LAUNCH_CHECK();
-    rc = read_counters(counters, host_ctr, stream);
-    if (rc) return rc;
-    const int64_t miss_lookups = host_ctr[kCtrMissLookups];
-    stats->unique_hits = host_ctr[kCtrUniqueHits];
-    stats->miss_lookups = miss_lookups;
-    auto clear_bitmap = [&]() { return cudaMemsetAsync(t->miss_bitmap, 0, (size_t)L.words * 4, stream); };
-    if (host_ctr[kCtrBadIndex]) {
-        clear_bitmap();
-        set_error("prepare_ids: an id is outside [0, %lld)", (long long)t->num_rows);
-        return CEBAG_ERR_INDEX;
-    }
-    if (miss_lookups > 0) {
-        // missed rows, ascending
-        {
-            KernelScope scope(kKernBitmapRank, stream);
-            bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums);
-            CEBAG_LAUNCH_CHECK();
-            rc = exclusive_scan_inplace(bitmap_sums, L.bitmap_blocks, counters + kCtrUniqueMisses, scan_ws, stream);
-            if (rc) return rc;
-        }
-        rc = read_counters(counters, host_ctr, stream);
+    {   // missed rows, ascending: count, then (after the verdict) emit
+        KernelScope scope(kKernBitmapRank, stream);
+        bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
+                                                                               counters + kCtrMissLookups);
+        CEBAG_LAUNCH_CHECK();
+        rc = exclusive_scan_inplace(bitmap_sums, L.bitmap_blocks, counters + kCtrUniqueMisses, scan_ws, stream);
         if (rc) return rc;
-        const int64_t M = host_ctr[kCtrUniqueMisses];
-        stats->unique_misses = M;
-        if (stats->unique_hits + M > C) {   // A.3 capacity assert, before any state changes
-            clear_bitmap();
-            set_error("You move %lld embedding rows from CPU to CUDA. It is larger than the capacity of the cache, "
-                      "which at most contains %lld rows, Please increase cuda_row_num or decrease the training batch size.",
-                      (long long)(stats->unique_hits + M), (long long)C);
-            return CEBAG_ERR_CAPACITY;
-        }
-        {
-            KernelScope scope(kKernBitmapRank, stream);
-            bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
-                                                                                  miss_rows, C);
+    }
+    {
+        KernelScope scope(kKernSelect, stream, t->protect_windows > 1 ? 2 : 1);
+        if (t->protect_windows > 1) count_evictable_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters);
+        decide_kernel<<<1, 256, 0, stream>>>(*t, counters, sel);
+        CEBAG_LAUNCH_CHECK();
+    }
+    {
+        KernelScope scope(kKernBitmapRank, stream);
+        bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
+                                                                              miss_rows, C, counters + kCtrAdmit);
+        CEBAG_LAUNCH_CHECK();
+    }
+    {   // victims: the E smallest keys (no-ops when E == 0)
+        KernelScope scope(kKernSelect, stream, lfu ? 17 : 8);
+        const int top = lfu ? 56 : 24;
+        for (int shift = top; shift >= 0; shift -= 8) {
+            select_hist_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters, sel, shift, shift == top);
+            select_choose_kernel<<<1, 256, 0, stream>>>(counters, sel, shift);
         }
         CEBAG_LAUNCH_CHECK();
-
-        const int64_t E = M > t->avail ? M - t->avail : 0;
-        const int sgrid = grid_for(C, kThreads, 8);
-        if (E > 0 && t->protect_windows > 1) {
-            // rows of an earlier, still protected window cannot be victims: make sure enough others exist
-            count_evictable_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters);
-            count_launches(1);
+        if (lfu) {   // ties at the threshold go to the lowest slots
+            select_equal_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters, sel, flags_b);
             CEBAG_LAUNCH_CHECK();
-            rc = read_counters(counters, host_ctr, stream);
-            if (rc) return rc;
-            if (E > host_ctr[kCtrEvictable]) {
-                clear_bitmap();
-                set_error("You move %lld embedding rows from CPU to CUDA while %d look-ahead windows are protected: only "
-                          "%lld of the %lld cached rows may be evicted but %lld are needed. It is larger than the capacity "
-                          "of the cache, Please increase cuda_row_num or decrease the training batch size.",
-                          (long long)(stats->unique_hits + M), t->protect_windows, (long long)host_ctr[kCtrEvictable],
-                          (long long)C, (long long)E);
-                return CEBAG_ERR_CAPACITY;
-            }
-        }
-        const bool lfu = t->strategy == CEBAG_EVICT_LFU;
-        if (E > 0) {
-            KernelScope scope(kKernSelect, stream, lfu ? 17 : 8);
-            SelectState init;
-            memset(&init, 0, sizeof(init));
-            init.k = E;
-            CEBAG_CUDA_CHECK(cudaMemcpyAsync(sel, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
-            const int top = lfu ? 56 : 24;
-            for (int shift = top; shift >= 0; shift -= 8) {
-                select_hist_kernel<<<sgrid, kThreads, 0, stream>>>(*t, sel, shift, shift == top);
-                select_choose_kernel<<<1, 256, 0, stream>>>(sel, shift);
-            }
-            CEBAG_LAUNCH_CHECK();
-            if (lfu) {   // ties at the threshold go to the lowest slots
-                select_equal_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, sel, flags_b);
-                CEBAG_LAUNCH_CHECK();
-                rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
-                if (rc) return rc;
-            }
-        }
-        {
-            KernelScope scope(kKernFreeSlots, stream, 2);
-            free_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, sel, (E > 0 && lfu) ? flags_b : nullptr,
-                                                              E > 0 ? 1 : 0, flags_a);
-            CEBAG_LAUNCH_CHECK();
-            // flags_b is free again: positions = exclusive scan of the flags
-            CEBAG_CUDA_CHECK(cudaMemcpyAsync(flags_b, flags_a, (size_t)C * 4, cudaMemcpyDeviceToDevice, stream));
             rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
             if (rc) return rc;
-            emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(flags_a, flags_b, C, free_slots, M);
-            CEBAG_LAUNCH_CHECK();
         }
-        {
-            KernelScope scope(kKernFreeSlots, stream);
-            commit_admission_kernel<<<grid_for(M, kThreads, 8), kThreads, 0, stream>>>(*t, miss_rows, free_slots,
-                                                                                     victim_rows, M);
-        }
-        CEBAG_LAUNCH_CHECK();
-        {
-            // PCIe-bound: ~56 GB/s x ~2 us of latency is ~110 KB in flight, a few hundred rows.  A SMALL grid matters:
-            // under the look-ahead driver these kernels run next to the fwd/bwd kernels, and measured step time falls
-            // from 0.71 to 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 47 of
-            // 51 GB/s).  With a copy stream in the workspace the rows move there while `stream` goes on with the
-            // map-only work.
-            static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
-            static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
-            cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
-            if (cstream != stream) {
-                cudaEvent_t committed;
-                CEBAG_CUDA_CHECK(cudaEventCreateWithFlags(&committed, cudaEventDisableTiming));
-                CEBAG_CUDA_CHECK(cudaEventRecord(committed, stream));
-                CEBAG_CUDA_CHECK(cudaStreamWaitEvent(cstream, committed, 0));
-                CEBAG_CUDA_CHECK(cudaEventDestroy(committed));   // released once the wait has been satisfied
-            }
-            const int64_t want = ceil_div(M * 32, swap_threads);
-            const int mgrid = (int)(want < swap_ctas ? want : swap_ctas);
-            const bool vec = table_vec_ok(t);
-            {
-                KernelScope scope(kKernSwapRows, cstream, E > 0 ? 2 : 1);
-                if (E > 0) {
-                    if (vec) copy_rows_kernel<true><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 1);
-                    else copy_rows_kernel<false><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 1);
-                }
-                if (vec) copy_rows_kernel<true><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 0);
-                else copy_rows_kernel<false><<<mgrid, swap_threads, 0, cstream>>>(*t, miss_rows, free_slots, victim_rows, M, 0);
-            }
-            if (cstream != stream && ws->copy_done_event)
-                CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->copy_done_event), cstream));
-        }
-        CEBAG_LAUNCH_CHECK();
-        {
-            KernelScope scope(kKernFixup, stream);
-            fixup_kernel<<<grid_for(miss_lookups, kThreads, 8), kThreads, 0, stream>>>(*t, ids, miss_pos, miss_lookups,
-                                                                                      slot_ids_out);
-        }
-        CEBAG_LAUNCH_CHECK();
-        stats->evicted = E;
-        t->avail += E - M;
     }
-    if (t->strategy == CEBAG_EVICT_LFU) {
+    {
+        KernelScope scope(kKernFreeSlots, stream, 4);
+        free_flags_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters, sel, lfu ? flags_b : nullptr, flags_a);
+        CEBAG_LAUNCH_CHECK();
+        // flags_b is free again: positions = exclusive scan of the flags
+        CEBAG_CUDA_CHECK(cudaMemcpyAsync(flags_b, flags_a, (size_t)C * 4, cudaMemcpyDeviceToDevice, stream));
+        rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
+        if (rc) return rc;
+        emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(counters, flags_a, flags_b, C, free_slots);
+        commit_admission_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, miss_rows,
+                                                                                            free_slots, victim_rows);
+        stamp_hits_kernel<<<grid_for(L.hit_words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.hit_words);
+        CEBAG_LAUNCH_CHECK();
+    }
+    {   // everything that only needs the maps: slot ids of the ids that missed, LFU counts, the result record
+        KernelScope scope(kKernFixup, stream);
+        fixup_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, stream>>>(*t, counters, ids, miss_pos, slot_ids_out);
+        CEBAG_LAUNCH_CHECK();
+    }
+    if (lfu) {
         KernelScope scope(kKernLfuCount, stream);
-        lfu_count_kernel<<<grid_for(ceil_div(n, kLfuTile) * kThreads, kThreads, 8), kThreads, 0, stream>>>(*t, slot_ids_out, n);
+        lfu_count_kernel<<<grid_for(ceil_div(n, kLfuTile) * kThreads, kThreads, 8), kThreads, 0, stream>>>(
+            *t, counters, slot_ids_out, n);
         CEBAG_LAUNCH_CHECK();
     }
+    {   // victims in ascending host-row order (flags_a) and the slots that still hold them (flags_b)
+        KernelScope scope(kKernVictimRank, stream, 6);
+        mark_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, victim_rows);
+        bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
+                                                                               counters + kCtrEvict);
+        CEBAG_LAUNCH_CHECK();
+        rc = exclusive_scan_inplace(bitmap_sums, L.bitmap_blocks, counters + kCtrVictims, scan_ws, stream);
+        if (rc) return rc;
+        bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
+                                                                              flags_a, C, counters + kCtrEvict);
+        resolve_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, flags_a, flags_b);
+        clear_bitmap_if_rejected_kernel<<<grid_for(L.words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.words);
+        end_call_kernel<<<1, 32, 0, stream>>>(*t, counters, n, result_dev);
+        CEBAG_LAUNCH_CHECK();
+    }
+
+    // ---- rows ---------------------------------------------------------------------------------------------------------
+    // PCIe-bound: ~50 GB/s x ~2 us of latency is ~110 KB in flight, a few hundred rows.  A SMALL grid matters: under
+    // the look-ahead driver these kernels run next to the fwd/bwd kernels, and measured step time falls from 0.71 to
+    // 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 46 of 51 GB/s).
+    static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
+    static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
+    cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
+    const bool park = cstream != stream && ws->stage != nullptr && ws->stage_rows > 0;
+    RowLists lists;
+    lists.miss_rows = miss_rows;
+    lists.free_slots = free_slots;
+    lists.victims_sorted = flags_a;
+    lists.victim_slots = flags_b;
+    lists.stage = park ? ws->stage : nullptr;
+    lists.stage_state = park ? ws->stage_state : nullptr;
+    lists.stage_rows = park ? ws->stage_rows : 0;
+    // the victims' rows (and the slots the fill overwrites) may still be in use by an earlier window
+    if (ws->victims_ready_event)
+        CEBAG_CUDA_CHECK(cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(ws->victims_ready_event), 0));
+    if (park) {
+        KernelScope scope(kKernPark, stream);
+        rc = launch_rows<kParkVictims>(t, counters, lists, kNumSMs * 4, kThreads, stream);   // HBM -> HBM
+        if (rc) return rc;
+    }
+    if (cstream != stream) {
+        // one event per host thread, re-recorded by every call: a wait captures the record that precedes it
+        static thread_local cudaEvent_t committed = nullptr;
+        if (!committed) CEBAG_CUDA_CHECK(cudaEventCreateWithFlags(&committed, cudaEventDisableTiming));
+        CEBAG_CUDA_CHECK(cudaEventRecord(committed, stream));
+        CEBAG_CUDA_CHECK(cudaStreamWaitEvent(cstream, committed, 0));
+    }
+    {   // victims that are not parked must leave their slots before the fill overwrites them
+        KernelScope scope(kKernWriteBack, cstream);
+        rc = launch_rows<kWriteDirect>(t, counters, lists, swap_ctas, swap_threads, cstream);
+        if (rc) return rc;
+    }
+    {
+        KernelScope scope(kKernFillRows, cstream);
+        rc = launch_rows<kFill>(t, counters, lists, swap_ctas, swap_threads, cstream);
+        if (rc) return rc;
+    }
+    if (cstream != stream && ws->copy_done_event)
+        CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->copy_done_event), cstream));
+    if (park) {
+        KernelScope scope(kKernWriteBack, cstream);
+        rc = launch_rows<kWriteParked>(t, counters, lists, swap_ctas, swap_threads, cstream);
+        if (rc) return rc;
+    }
+    if (cstream != stream && ws->writeback_done_event)
+        CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->writeback_done_event), cstream));
     return CEBAG_OK;
 }
 
-extern "C" int cebag_flush(cebag_table* t, const cebag_workspace* ws, int64_t* rows_written, void* stream_) {
+extern "C" int cebag_prepare_result_status(const cebag_table* t, const cebag_prepare_result* r,
+                                           cebag_prepare_stats* stats) {
+    CEBAG_REQUIRE(t != nullptr && r != nullptr, "table / result");
+    const int64_t status = *reinterpret_cast<const volatile int64_t*>(&r->status);
+    if (status == CEBAG_PREPARE_PENDING) return CEBAG_PREPARE_PENDING;
+    if (stats) {
+        stats->unique_hits = r->unique_hits;
+        stats->unique_misses = r->unique_misses;
+        stats->evicted = r->evicted;
+        stats->miss_lookups = r->miss_lookups;
+        stats->total_lookups = r->total_lookups;
+    }
+    if (status == CEBAG_ERR_INDEX) {
+        set_error("prepare_ids: an id is outside [0, %lld)", (long long)t->num_rows);
+    } else if (status == CEBAG_ERR_CAPACITY) {
+        const long long need = (long long)(r->unique_hits + r->unique_misses);
+        if (need > (long long)t->cache_rows)
+            set_error("You move %lld embedding rows from CPU to CUDA. It is larger than the capacity of the cache, "
+                      "which at most contains %lld rows, Please increase cuda_row_num or decrease the training batch size.",
+                      need, (long long)t->cache_rows);
+        else
+            set_error("You move %lld embedding rows from CPU to CUDA while %d look-ahead windows are protected: only "
+                      "%lld of the %lld cached rows may be evicted. It is larger than the capacity of the cache, Please "
+                      "increase cuda_row_num or decrease the training batch size.",
+                      need, t->protect_windows, (long long)r->evictable, (long long)t->cache_rows);
+    }
+    return (int)status;
+}
+
+extern "C" int cebag_prepare_ids(const cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
+                                 const cebag_workspace* ws, cebag_prepare_stats* stats, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(ws && ws->pinned && stats, "workspace / stats");
+    cebag_prepare_result* result = reinterpret_cast<cebag_prepare_result*>(ws->pinned);
+    int rc = cebag_prepare_ids_async(t, ids, n, slot_ids_out, ws, result, stream);
+    if (rc) return rc;
+    CEBAG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return cebag_prepare_result_status(t, result, stats);
+}
+
+extern "C" int cebag_available_rows(const cebag_table* t, int64_t* avail_out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int rc = check_table(t);
+    if (rc) return rc;
+    CEBAG_REQUIRE(avail_out != nullptr, "avail_out");
+    int64_t state[CEBAG_STATE_WORDS];
+    rc = read_state(t, state, stream);
+    if (rc) return rc;
+    *avail_out = state[CEBAG_STATE_AVAIL];
+    return CEBAG_OK;
+}
+
+extern "C" int cebag_flush(const cebag_table* t, const cebag_workspace* ws, int64_t* rows_written, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_table(t);
     if (rc) return rc;
@@ -684,47 +933,50 @@ extern "C" int cebag_flush(cebag_table* t, const cebag_workspace* ws, int64_t* r
         else flush_kernel<false><<<grid, kThreads, 0, stream>>>(*t, counters);
     }
     CEBAG_LAUNCH_CHECK();
-    rc = read_counters(counters, reinterpret_cast<int32_t*>(ws->pinned), stream);
-    if (rc) return rc;
+    CEBAG_CUDA_CHECK(cudaMemcpyAsync(ws->pinned, counters, kNumCounters * 4, cudaMemcpyDeviceToHost, stream));
+    CEBAG_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (rows_written) *rows_written = reinterpret_cast<int32_t*>(ws->pinned)[kCtrFlushed];
-    t->avail = t->cache_rows;
-    t->epoch = 0;
     return CEBAG_OK;
 }
 
-extern "C" int cebag_preload(cebag_table* t, const int32_t* rows, const int64_t* freq_init, int64_t k, void* stream_) {
+extern "C" int cebag_preload(const cebag_table* t, const int32_t* rows, const int64_t* freq_init, int64_t k, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_table(t);
     if (rc) return rc;
-    CEBAG_REQUIRE(k >= 0 && k <= t->cache_rows && k <= t->avail, "preload count");
-    CEBAG_REQUIRE(t->avail == t->cache_rows, "preload needs an empty cache");
+    int64_t state[CEBAG_STATE_WORDS];
+    rc = read_state(t, state, stream);
+    if (rc) return rc;
+    CEBAG_REQUIRE(k >= 0 && k <= t->cache_rows, "preload count");
+    CEBAG_REQUIRE(state[CEBAG_STATE_AVAIL] == t->cache_rows, "preload needs an empty cache");
     if (k == 0) return CEBAG_OK;
     CEBAG_REQUIRE(rows != nullptr, "rows");
     const int grid = grid_for(k * 32, kThreads, 8);
     {
-        KernelScope scope(kKernMoveRows, stream);
+        KernelScope scope(kKernMoveRows, stream, 2);
         if (table_vec_ok(t)) move_rows_kernel<true><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
         else move_rows_kernel<false><<<grid, kThreads, 0, stream>>>(*t, rows, nullptr, freq_init, k, 0);
+        add_avail_kernel<<<1, 1, 0, stream>>>(*t, -(long long)k);
     }
     CEBAG_LAUNCH_CHECK();
-    t->avail -= k;
     return CEBAG_OK;
 }
 
-extern "C" int cebag_admit_row(cebag_table* t, int64_t row, int64_t slot, void* stream_) {
+extern "C" int cebag_admit_row(const cebag_table* t, int64_t row, int64_t slot, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_table(t);
     if (rc) return rc;
     CEBAG_REQUIRE(row >= 0 && row < t->num_rows && slot >= 0 && slot < t->cache_rows, "row / slot");
-    CEBAG_REQUIRE(t->avail > 0, "no free slot");
+    int64_t state[CEBAG_STATE_WORDS];
+    rc = read_state(t, state, stream);
+    if (rc) return rc;
+    CEBAG_REQUIRE(state[CEBAG_STATE_AVAIL] > 0, "no free slot");
     count_launches(1);
     move_one_kernel<<<1, 32, 0, stream>>>(*t, (int32_t)row, (int32_t)slot, 0, table_vec_ok(t) ? 1 : 0);
     CEBAG_LAUNCH_CHECK();
-    t->avail -= 1;
     return CEBAG_OK;
 }
 
-extern "C" int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream_) {
+extern "C" int cebag_evict_slot(const cebag_table* t, int64_t slot, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     int rc = check_table(t);
     if (rc) return rc;
@@ -732,6 +984,5 @@ extern "C" int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream_) {
     count_launches(1);
     move_one_kernel<<<1, 32, 0, stream>>>(*t, -1, (int32_t)slot, 1, table_vec_ok(t) ? 1 : 0);
     CEBAG_LAUNCH_CHECK();
-    t->avail += 1;
     return CEBAG_OK;
 }

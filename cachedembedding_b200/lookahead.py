@@ -5,20 +5,26 @@ through them (/root/reference/recsys/dlrm_main.py:245-266); every cache operatio
 timers end in torch.cuda.synchronize()).  Here three streams work at once:
 
   compute stream : forward / backward of window k (the caller's current stream)
-  side stream    : prepare_ids of window k+1 -- id->slot probe, victim selection, map commit, LFU update -- and, if
-                   asked, the gradient-independent half of each batch's fused backward (radix sort by slot)
-  copy stream    : the PCIe row traffic of that prepare_ids (write-back of victims, fill of missed rows), which only the
-                   forward of window k+1 has to wait for
+  side stream    : prepare_ids of window k+1 -- id->slot probe, victim selection, map commit, LFU update, parking of
+                   the victims in an HBM staging buffer -- and, if asked, the gradient-independent half of each
+                   batch's fused backward (radix sort by slot)
+  copy stream    : the PCIe row traffic of that prepare_ids (fill of the missed rows, then write-back of the parked
+                   victims); only the fill is waited for by the forward of window k+1
+
+prepare_ids never waits for the GPU (cebag_prepare_ids_async), so `submit` costs the host a few dozen kernel launches
+and may be called anywhere inside window k -- the earlier the better: right after the window's first step has been
+enqueued.
 
 Hazards and how they are closed:
   * rows the in-flight window k still reads/updates must not be evicted by prepare(k+1): the manager protects the
     slots stamped by the last TWO windows (`protect_windows = 2`); the capacity rule becomes
-    |rows(k) U rows(k+1)| <= cuda_row_num, checked before anything is changed;
-  * a victim may have been updated by window k-1's backward: the stream that moves rows (the copy stream, ordered
-    after the side stream's map commit) waits for the event recorded after window k-1's compute was enqueued; the
-    map-only head of prepare_ids does not touch rows and is not held back;
+    |rows(k) U rows(k+1)| <= cuda_row_num, checked on the device before anything is changed;
+  * a victim of prepare(k+1) may have been updated by window k-1's backward: the side stream waits for the event
+    recorded after window k-1's compute was enqueued before it parks the victims (cebag_workspace.victims_ready_event);
+    the map-only part of prepare_ids does not touch rows and is not held back;
   * slot ids (side stream) and rows (copy stream) are consumed on the compute stream: `PrefetchHandle.wait()` makes it
-    wait for both completion events;
+    wait for both completion events -- and makes the HOST wait for the call's result record, so that a window that
+    does not fit the cache raises there, before any of its batches is enqueued;
   * backward-plan buffers are a ring of two windows owned by this object: the buffers of window k-1 are reused for
     window k+1 only after the same fence.
 Pooled sums and updated rows are unaffected by which victims are chosen (the cache is transparent); the slot maps
@@ -26,20 +32,23 @@ follow the oracle run with the same two-window protection (tests/test_gpu_parity
 """
 from __future__ import annotations
 
-from collections import deque
 from typing import Optional
 
 import torch
 
 
 class PrefetchHandle:
-    def __init__(self, slot_ids: torch.Tensor, done: torch.cuda.Event, rows_done: Optional[torch.cuda.Event]):
+    def __init__(self, mgr, slot_ids: torch.Tensor, done: torch.cuda.Event, rows_done: Optional[torch.cuda.Event]):
+        self._mgr = mgr
         self._slot_ids = slot_ids
         self._done = done
         self._rows_done = rows_done
 
     def wait(self) -> torch.Tensor:
-        """Slot ids of the window; the current stream waits (on the device) for the cache operation to finish."""
+        """Slot ids of the window.  The host waits for the result record of the call (a few bytes written by its last
+        map kernel; raises CacheCapacityError / IndexError if the device rejected the window); the current stream
+        waits, on the device, for the slot ids and for the missed rows."""
+        self._mgr._harvest()
         cur = torch.cuda.current_stream()
         cur.wait_event(self._done)
         if self._rows_done is not None:
@@ -54,11 +63,13 @@ class LookaheadPrefetcher:
     h = pf.submit(ids_of_window_0)
     for k in range(num_windows):
         slot_ids = h.wait()
-        ... forward / backward of the window's batches with bag.set_cache_op(False) ...
-        pf.window_enqueued()
+        ... first forward / backward of the window, with bag.set_cache_op(False) ...
         if k + 1 < num_windows:
-            h = pf.submit(ids_of_window_k_plus_1)      # overlaps the work just enqueued
+            h = pf.submit(ids_of_window_k_plus_1)      # overlaps this window's compute
+        ... the other forward / backward steps of the window ...
+        pf.window_enqueued()
     pf.close()
+    (Submitting after `window_enqueued()` -- the round-1 order -- still works; it just starts the overlap later.)
     """
 
     def __init__(self, bag_or_mgr, priority: int = -1, copy_stream: bool = True):
@@ -67,11 +78,14 @@ class LookaheadPrefetcher:
         self.device = self.mgr.device
         self.stream = torch.cuda.Stream(device=self.device, priority=priority)
         self.copy_stream = torch.cuda.Stream(device=self.device, priority=priority) if copy_stream else None
-        self._fences = deque(maxlen=2)     # events after the compute of the last two windows
         self._saved_protect = self.mgr.protect_windows
+        self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
+        self.mgr._defer_results = True
         self._plan_ring = [[], []]         # backward-plan workspaces of the even / odd windows
-        self._window = 0
+        self._fences = {}                  # window index -> event recorded after its compute was enqueued
+        self._submitted = 0                # windows submitted since the last drain
+        self._enqueued = 0                 # windows whose compute has been enqueued since the last drain
 
     def _plan_buffer(self, parity: int, j: int, nbytes: int) -> torch.Tensor:
         ring = self._plan_ring[parity]
@@ -80,6 +94,17 @@ class LookaheadPrefetcher:
         if ring[j] is None or ring[j].numel() < nbytes:
             ring[j] = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
         return ring[j]
+
+    def _victims_fence(self, w: int) -> torch.cuda.Event:
+        """What the row traffic of window w has to wait for: the compute of window w-2 (victims are never taken from the
+        last two windows).  Before the driver has seen two windows enqueued -- at start, after drain(), or when the
+        caller does not report its windows -- an event recorded now on the current stream stands in: whatever ran on
+        the cache before this driver took over is then finished as well."""
+        ev = self._fences.get(w - 2)
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        return ev
 
     def submit(self, ids, ready: Optional[torch.cuda.Event] = None, offsets=None, layout="bag_major",
                layout_batch=0) -> PrefetchHandle:
@@ -90,66 +115,69 @@ class LookaheadPrefetcher:
 
         Device ids must be complete when the side stream starts reading them.  Pass `ready` = an event recorded right
         after they were produced; without it nothing is waited for (recording an event here would be too late: the
-        current stream already holds the whole window that this call is supposed to overlap)."""
+        current stream already holds the window that this call is supposed to overlap)."""
         side = self.stream
+        mgr = self.mgr
         if ready is not None:
             side.wait_event(ready)
-        # window k-1 must have finished before its rows can be written back (its updates have to be in them) and
-        # before its plan buffers are recycled.  Only the ROW COPIES need that: with a copy stream the map-only head
-        # of prepare_ids (probe, victim selection, commit) starts at once and just the copy stream is fenced.
-        fence = self._fences[0] if len(self._fences) == 2 else None
-        rows_done = None
-        if self.copy_stream is not None:
-            if fence is not None:
-                self.copy_stream.wait_event(fence)
-            rows_done = torch.cuda.Event()
-            rows_done.record(self.copy_stream)     # instantiates the event; re-recorded after the row copies
-            self.mgr._copy_stream, self.mgr._copy_done = self.copy_stream, rows_done
-        elif fence is not None:
+        w = self._submitted
+        self._submitted += 1
+        fence = self._victims_fence(w)
+        parity = w & 1
+        mgr._copy_stream, mgr._victims_ready = self.copy_stream, fence
+        if self.copy_stream is None:
             side.wait_event(fence)
-        parity = self._window & 1
-        self._window += 1
         try:
             with torch.cuda.stream(side):
                 parts = ids if isinstance(ids, (list, tuple)) else [ids]
                 parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
                 ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
-                slot_ids = self.mgr.prepare_ids(ids_dev)
+                slot_ids = mgr.prepare_ids(ids_dev)
+                rows_done = mgr._rows_ready
+                mgr._rows_ready = None             # the handle carries it; forward() of the bag need not wait again
                 if offsets is not None and self.bag is not None:
                     # the gradient-independent half of every batch's fused backward also runs here, off the critical
-                    # path; splitting by the batches' own sizes gives the views the training loop passes to forward
-                    if fence is not None and self.copy_stream is not None:
-                        side.wait_event(fence)     # plan buffers of window k-1 are free again
+                    # path (the side stream has passed the fence by now: the plan buffers of window w-2 are free);
+                    # splitting by the batches' own sizes gives the views the training loop passes to forward
                     offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
+                    self.bag.drop_backward_plans(parity)
                     for j, (chunk, off) in enumerate(zip(torch.split(slot_ids, [t.numel() for t in parts]), offs)):
-                        self.bag.plan_backward(chunk, off, layout, layout_batch,
+                        self.bag.plan_backward(chunk, off, layout, layout_batch, tag=parity,
                                                workspace_factory=lambda n, p=parity, j=j: self._plan_buffer(p, j, n))
                 done = torch.cuda.Event()
                 done.record(side)
         finally:
-            self.mgr._copy_stream, self.mgr._copy_done = None, None
+            mgr._copy_stream, mgr._victims_ready = None, None
         for t in parts:
             if t.is_cuda:
                 t.record_stream(side)
-        return PrefetchHandle(slot_ids, done, rows_done)
+        return PrefetchHandle(mgr, slot_ids, done, rows_done)
 
     def window_enqueued(self):
         """Call after the forward/backward of the current window has been enqueued on the compute stream."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        self._fences.append(ev)
+        self._fences[self._enqueued] = ev
+        self._fences.pop(self._enqueued - 3, None)
+        self._enqueued += 1
 
     def drain(self):
-        """Wait for everything submitted so far; the driver stays usable (streams, plan buffers and protection kept)."""
+        """Wait for everything submitted so far -- side stream, copy stream and the compute the fences stand for; the
+        driver stays usable (streams, plan buffers and protection kept)."""
         self.stream.synchronize()
         if self.copy_stream is not None:
             self.copy_stream.synchronize()
+        for ev in self._fences.values():
+            ev.synchronize()
+        self.mgr._harvest()
         self._fences.clear()
+        self._submitted = self._enqueued = 0
 
     def close(self):
-        """Back to the reference's one-window protection (waits for the side and copy streams)."""
-        self.stream.synchronize()
-        if self.copy_stream is not None:
-            self.copy_stream.synchronize()
+        """Back to the reference's one-window protection (waits like drain())."""
+        self.drain()
         self.mgr.protect_windows = self._saved_protect
+        self.mgr._defer_results = self._saved_defer
+        if self.bag is not None:
+            self.bag.drop_backward_plans()
         self._plan_ring = [[], []]

@@ -138,6 +138,7 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         offsets = offsets.to(slot_ids.device)
         if offsets.dtype not in (torch.int32, torch.int64):
             offsets = offsets.long()
+        self.cache_weight_mgr.wait_rows()
         out = _FusedTablewiseFunction.apply(self.cache_weight_mgr.cuda_cached_weight, slot_ids.contiguous().view(-1),
                                             offsets.contiguous(), self, exch)
         return out

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 5
+#define CEBAG_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -55,41 +55,59 @@ enum { CEBAG_LAYOUT_BAG_MAJOR = 0,     /* out[g, :]                       -- wha
  *   weight -> host_table, cuda_cached_weight -> cache, idx_map, cached_idx_map -> slot2row,
  *   inverted_cached_idx -> row2slot, freq_cnter -> freq.
  * B200-first differences: the id maps are int32 (half the HBM of the reference's int64 maps, which were 76 % of
- * its footprint); idx_map may be NULL (identity) ; a per-slot window stamp and a per-row miss
- * bitmap replace the reference's sort-based unique/isin.
+ * its footprint); idx_map may be NULL (identity); a per-slot window stamp, a per-slot hit bitmap
+ * and a per-row miss bitmap replace the reference's sort-based unique/isin; the free-slot count and the window stamp
+ * live in DEVICE memory (dev_state), so that prepare_ids never has to wait for the GPU.
  */
+enum { CEBAG_STATE_AVAIL = 0,   /* free slots (upstream _cuda_available_row_num)                        */
+       CEBAG_STATE_EPOCH = 1,   /* window stamp of the last successful prepare_ids                      */
+       CEBAG_STATE_CALLS = 2,   /* prepare_ids calls that completed on the device, successful or not    */
+       CEBAG_STATE_WORDS = 8 };
+
 typedef struct cebag_table {
     int64_t   num_rows;       /* N: rows of the host table                                                */
     int32_t   dim;            /* D: floats per row                                                        */
     int32_t   cache_rows;     /* C: slots in HBM                                                          */
     int32_t   strategy;       /* CEBAG_EVICT_*                                                            */
-    int32_t   epoch;          /* window stamp, advanced by every prepare_ids (library-maintained)         */
     int32_t   protect_windows;/* slots stamped by the last `protect_windows` prepare_ids calls are never evicted:
                                  1 = the reference's rule (only the current call's rows, A.4);
                                  2 = look-ahead overlap: the previous window may still be computing on them    */
-    int32_t   reserved0;
-    int64_t   avail;          /* free slots (library-maintained; upstream _cuda_available_row_num)        */
     float*    host_table;     /* fp32[N, D]  pinned host memory, device-visible address                   */
     float*    host_state;     /* fp32[N]     row-wise Adagrad state in pinned host memory, or NULL        */
     float*    cache;          /* fp32[C, D]  HBM                                                          */
     float*    cache_state;    /* fp32[C]     HBM, or NULL                                                 */
     const int32_t* idx_map;   /* int32[N] id -> row, or NULL for identity                                 */
-    int32_t*  row2slot;       /* int32[N]   -1 = not resident                                             */
+    int32_t*  row2slot;       /* int32[N]   < 0 = not resident (-1; values <= -2 are transient markers of
+                                 rows being written back)                                                 */
     int32_t*  slot2row;       /* int32[C]   -1 = empty                                                    */
     int64_t*  freq;           /* int64[C]   LFU counters (CEBAG_FREQ_EMPTY = empty); NULL for DATASET     */
     int32_t*  slot_epoch;     /* int32[C]   stamp of the last prepare_ids window that used the slot       */
     uint32_t* miss_bitmap;    /* uint32[ceil(N/32)] all-zero between calls                                */
+    uint32_t* hit_bitmap;     /* uint32[ceil(C/32)] all-zero between calls                                */
+    int64_t*  dev_state;      /* int64[CEBAG_STATE_WORDS] HBM; [AVAIL] = C and the rest 0 for an empty cache */
 } cebag_table;
 
-/* Scratch for one prepare_ids / flush call; sizes from cebag_prepare_workspace_bytes(). */
+/* Scratch and stream plumbing of one prepare_ids / flush call; sizes from cebag_prepare_workspace_bytes().
+ * Everything a call enqueues reads its row lists from `device`: the buffer must stay untouched until the work has
+ * run (until writeback_done_event when a copy stream is used). */
 typedef struct cebag_workspace {
     void*  device;            /* device scratch                                                           */
     size_t device_bytes;
-    void*  pinned;            /* >= 256 bytes of pinned host memory for counter read-back                 */
-    void*  copy_stream;       /* optional cudaStream_t: the PCIe row copies of prepare_ids are enqueued here (after the
-                                 maps are committed on `stream`) instead of on `stream`; the workspace must then stay
-                                 alive until copy_done_event has completed                                     */
-    void*  copy_done_event;   /* optional cudaEvent_t recorded on copy_stream after the row copies               */
+    void*  pinned;            /* >= 256 bytes of pinned, device-mapped host memory (result read-back of the
+                                 synchronous entry points)                                                */
+    void*  copy_stream;       /* optional cudaStream_t: the PCIe row traffic of prepare_ids (fill of the missed rows,
+                                 write-back of the victims) is enqueued here, after the maps are committed on
+                                 `stream`, instead of on `stream`                                             */
+    void*  copy_done_event;   /* optional cudaEvent_t recorded on copy_stream once the missed rows are in HBM:
+                                 what the forward of the window has to wait for                              */
+    void*  writeback_done_event; /* optional cudaEvent_t recorded on copy_stream after the victims have reached the
+                                 host table (and `device` / `stage` may be reused)                           */
+    void*  victims_ready_event;  /* optional cudaEvent_t: `stream` waits for it before the victims' rows are read
+                                 (their last optimizer update may belong to an earlier, still running window)   */
+    float* stage;             /* optional fp32[stage_rows, D] HBM (copy_stream only): victims are parked here so that
+                                 the fill does not wait for their write-back over PCIe                        */
+    float* stage_state;       /* fp32[stage_rows] or NULL (row-wise Adagrad state of the parked victims)   */
+    int64_t stage_rows;
 } cebag_workspace;
 
 /* What one prepare_ids call did (upstream: num_hits_history / num_miss_history / num_write_back_history,
@@ -101,6 +119,16 @@ typedef struct cebag_prepare_stats {
     int64_t miss_lookups;     /* ids (with multiplicity) whose row was not resident                       */
     int64_t total_lookups;    /* n                                                                        */
 } cebag_prepare_stats;
+
+/* Result record of cebag_prepare_ids_async: written by the DEVICE into pinned, device-mapped host memory when the
+ * call's map work has run; `status` is CEBAG_PREPARE_PENDING until then. */
+#define CEBAG_PREPARE_PENDING (-1)
+typedef struct cebag_prepare_result {
+    int64_t status;           /* CEBAG_OK, CEBAG_ERR_CAPACITY, CEBAG_ERR_INDEX or CEBAG_PREPARE_PENDING   */
+    int64_t unique_hits, unique_misses, evicted, miss_lookups, total_lookups;
+    int64_t evictable;        /* occupied slots outside the protected windows (protect_windows > 1)       */
+    int64_t avail_after;      /* free slots after the call                                                */
+} cebag_prepare_result;
 
 CEBAG_API int         cebag_abi_version(void);
 CEBAG_API const char* cebag_last_error(void);
@@ -141,22 +169,35 @@ CEBAG_API size_t cebag_prepare_workspace_bytes(const cebag_table* t, int64_t n_i
 /* CachedParamMgr.prepare_ids(ids) (A.3 + A.4; called at recsys/dlrm_main.py:259 and inside forward when cache_op).
  * ids: int64[n] on the device.  slot_ids_out: int64[n] on the device, slot of every id, same order.
  * Performs unique / miss detection / victim selection / write-back of victims to the host table / fill of missed
- * rows / map + LFU counter update.  Synchronises `stream` once (counter read-back) before any state is changed,
- * so a CEBAG_ERR_CAPACITY / CEBAG_ERR_INDEX return leaves the table untouched; `stats` is filled either way. */
-CEBAG_API int cebag_prepare_ids(cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
+ * rows / map + LFU counter update.
+ *
+ * cebag_prepare_ids_async only ENQUEUES work and never waits for the GPU: every size the kernels need (misses,
+ * evictions, free slots) stays in device memory, grids are upper bounds, and the state-changing kernels are
+ * conditional on a device-side verdict -- an id out of range or a window that does not fit the cache (A.3 assert)
+ * leaves the table exactly as it was (slot_ids_out is then unspecified).  `result` (pinned, device-mapped) is set to
+ * PENDING by the call and filled in stream order; cebag_prepare_result_status() turns it into a status + message.
+ * cebag_prepare_ids = the same + one wait for `stream` at the end, returning the verdict and `stats`. */
+CEBAG_API int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
+                            const cebag_workspace* ws, cebag_prepare_result* result, void* stream);
+CEBAG_API int cebag_prepare_result_status(const cebag_table* t, const cebag_prepare_result* result,
+                            cebag_prepare_stats* stats_out);
+CEBAG_API int cebag_prepare_ids(const cebag_table* t, const int64_t* ids, int64_t n, int64_t* slot_ids_out,
                       const cebag_workspace* ws, cebag_prepare_stats* stats, void* stream);
 
 /* CachedParamMgr.flush() (A.1): write every resident row (and state) back to the host table, empty the maps.
  * Returns the number of rows written in *rows_written.  Synchronises `stream`. */
-CEBAG_API int cebag_flush(cebag_table* t, const cebag_workspace* ws, int64_t* rows_written, void* stream);
+CEBAG_API int cebag_flush(const cebag_table* t, const cebag_workspace* ws, int64_t* rows_written, void* stream);
 
 /* Warm-up preload of CachedParamMgr.reorder() (A.1 step 2): rows[k] (int32, device) go to slots 0..k-1;
  * freq_init (int64[k], device) seeds the LFU counters, NULL means 0.  The cache must be empty. */
-CEBAG_API int cebag_preload(cebag_table* t, const int32_t* rows, const int64_t* freq_init, int64_t k, void* stream);
+CEBAG_API int cebag_preload(const cebag_table* t, const int32_t* rows, const int64_t* freq_init, int64_t k, void* stream);
 
 /* Single-row legacy helpers of upstream test_cachemgr (B.1): _admit(row) into `slot`, _evict of `slot`. */
-CEBAG_API int cebag_admit_row(cebag_table* t, int64_t row, int64_t slot, void* stream);
-CEBAG_API int cebag_evict_slot(cebag_table* t, int64_t slot, void* stream);
+CEBAG_API int cebag_admit_row(const cebag_table* t, int64_t row, int64_t slot, void* stream);
+CEBAG_API int cebag_evict_slot(const cebag_table* t, int64_t slot, void* stream);
+
+/* Free slots right now (waits for `stream`; upstream cuda_available_row_num). */
+CEBAG_API int cebag_available_rows(const cebag_table* t, int64_t* avail_out, void* stream);
 
 /* Peer buffers of the fused pooled-embedding exchange (replaces dual_all_to_all_tablewise, A.6 / SURVEY K15).
  * Rank j owns samples [start_j, start_j + B_j) of the global batch B (torch.tensor_split rule: the first B % world

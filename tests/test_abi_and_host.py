@@ -33,6 +33,63 @@ def test_library_exports_every_declared_symbol():
     assert exported == declared
 
 
+def test_struct_layouts_and_constants_match_header(tmp_path):
+    """A C program compiled against include/cebag.h prints sizeof / offsetof of every struct and the value of every
+    constant; the ctypes mirror in _lib.py (what every call in this repo goes through) must agree byte for byte."""
+    import ctypes
+    import subprocess
+    from cachedembedding_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cebag.h")).read()
+    structs = {"cebag_table": _lib.Table, "cebag_workspace": _lib.Workspace, "cebag_prepare_stats": _lib.PrepareStats,
+               "cebag_prepare_result": _lib.PrepareResult, "cebag_exchange": _lib.Exchange,
+               "cebag_bag_args": _lib.BagArgs}
+    declared = re.findall(r"typedef struct (\w+) \{(.*?)\} \1;", header, flags=re.S)
+    assert sorted(n for n, _ in declared) == sorted(structs), "a struct of the header has no ctypes mirror"
+    for name, body in declared:   # same field names, same order
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(",")
+            first = re.search(r"(\w+)\s*(\[\w+\])?$", names[0].strip()).group(1)
+            fields.append(first)
+            fields += [re.search(r"(\w+)", n).group(1) for n in names[1:]]
+        assert fields == [f for f, _ in structs[name]._fields_], name
+    consts = {"CEBAG_ABI_VERSION": _lib.ABI_VERSION, "CEBAG_OK": _lib.OK, "CEBAG_ERR_INVALID": _lib.ERR_INVALID,
+              "CEBAG_ERR_CUDA": _lib.ERR_CUDA, "CEBAG_ERR_CAPACITY": _lib.ERR_CAPACITY, "CEBAG_ERR_INDEX": _lib.ERR_INDEX,
+              "CEBAG_PREPARE_PENDING": _lib.PREPARE_PENDING, "CEBAG_EVICT_LFU": _lib.EVICT_LFU,
+              "CEBAG_EVICT_DATASET": _lib.EVICT_DATASET, "CEBAG_MODE_SUM": _lib.MODE_SUM, "CEBAG_MODE_MEAN": _lib.MODE_MEAN,
+              "CEBAG_OPT_SGD": _lib.OPT_SGD, "CEBAG_OPT_ROWWISE_ADAGRAD": _lib.OPT_ROWWISE_ADAGRAD,
+              "CEBAG_MAX_PEERS": _lib.MAX_PEERS, "CEBAG_LAYOUT_BAG_MAJOR": _lib.LAYOUT_BAG_MAJOR,
+              "CEBAG_LAYOUT_SAMPLE_MAJOR": _lib.LAYOUT_SAMPLE_MAJOR, "CEBAG_LAYOUT_EXCHANGE": _lib.LAYOUT_EXCHANGE,
+              "CEBAG_STATE_AVAIL": _lib.STATE_AVAIL, "CEBAG_STATE_EPOCH": _lib.STATE_EPOCH,
+              "CEBAG_STATE_CALLS": _lib.STATE_CALLS, "CEBAG_STATE_WORDS": _lib.STATE_WORDS}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "cebag.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    for cname in consts:
+        lines.append(f'  printf("{cname} %lld\\n", (long long)({cname}));')
+    lines.append('  printf("CEBAG_FREQ_EMPTY %lld\\n", (long long)CEBAG_FREQ_EMPTY);')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)   # the header is plain C
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    for cname, value in consts.items():
+        assert int(got[cname]) == value, cname
+    assert int(got["CEBAG_FREQ_EMPTY"]) == _lib.FREQ_EMPTY
+
+
 def test_no_cpu_fallback():
     import cachedembedding_b200 as ce
     if torch.cuda.is_available():

@@ -441,9 +441,13 @@ def test_module_surface():
 
 # ---------------------------------------------------------------------------------------------------- look-ahead overlap
 @pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
-def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy):
+@pytest.mark.parametrize("early,stage_rows", [(True, 0), (False, 0), (True, 7)])
+def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy, early, stage_rows):
     """prepare_ids of window k+1 on a side stream while window k trains: slot ids and maps bit-exact against the
-    oracle run with the same two-window protection; pooled sums / final table within 1e-5 of it."""
+    oracle run with the same two-window protection; pooled sums / final table within 1e-5 of it.
+    early: window k+1 is submitted right after the FIRST step of window k (the order bench.py uses), otherwise after its
+    last step.  stage_rows = 7: most victims do not fit the staging buffer and are written back straight from their
+    slots before the fill."""
     ce = _mods()
     gen = torch.Generator().manual_seed(33)
     N, D, F, B, P = 6000, 128, 4, 64, 2
@@ -460,6 +464,7 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     offsets = torch.arange(F * B + 1)
     windows = [[(torch.rand(F * B, generator=gen) ** 2 * N).long().clamp_(0, N - 1) for _ in range(P)] for _ in range(8)]
     grads = [[torch.randn(F * B, D, generator=gen) for _ in range(P)] for _ in range(8)]
+    model.cache_weight_mgr.stage_rows = stage_rows
     pf = ce.LookaheadPrefetcher(model)
     assert model.cache_weight_mgr.protect_windows == 2
     h = pf.submit([w.pin_memory() for w in windows[0]], offsets=offsets.cuda())   # host ids: H2D rides the side stream
@@ -467,12 +472,14 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
         slots = h.wait()
         oslots = omodel.cache_weight_mgr.prepare_ids(torch.cat(windows[k]))
         outs = []
-        for s, g in zip(torch.chunk(slots, P), grads[k]):
+        for j, (s, g) in enumerate(zip(torch.chunk(slots, P), grads[k])):
             out = model(s, offsets.cuda())
             out.backward(g.cuda())
             outs.append(out)
+            if early and j == 0 and k + 1 < len(windows):
+                h = pf.submit([w.cuda() for w in windows[k + 1]], offsets=offsets.cuda())
         pf.window_enqueued()
-        if k + 1 < len(windows):
+        if not early and k + 1 < len(windows):
             h = pf.submit([w.cuda() for w in windows[k + 1]], offsets=offsets.cuda())
         assert torch.equal(slots.cpu(), oslots), f"slot ids differ in window {k}"
         for s, g, out in zip(torch.chunk(oslots, P), grads[k], outs):
@@ -533,6 +540,108 @@ def test_two_window_protection_capacity_error():
     assert int((mgr.cached_idx_map >= 0).sum()) == 10
     s = mgr.prepare_ids(torch.arange(20, 25).cuda())         # 5 victims fit
     assert torch.equal(mgr.cached_idx_map[s].cpu(), torch.arange(20, 25))
+
+
+def test_rejected_call_leaves_no_trace_with_two_window_protection():
+    """A window the device rejects (capacity, id out of range) changes nothing: maps, counters, stamps and the
+    protected windows are what they were, so the retry sees the same evictable set as the oracle."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(4)
+    N, D = 400, 8
+    weight = torch.randn(N, D, generator=gen)
+    kw = dict(mode="sum", include_last_offset=True, cache_ratio=0.1, warmup_ratio=0.0)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=ce.EvictionStrategy.LFU, **kw)
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=OStrategy.LFU, **kw)
+    mgr, omgr = model.cache_weight_mgr, omodel.cache_weight_mgr
+    mgr.protect_windows = omgr.protect_windows = 2
+    calls = [torch.arange(0, 20), torch.arange(15, 35), torch.arange(100, 130), torch.arange(30, 45),
+             torch.tensor([3, N + 5]), torch.arange(200, 215), torch.arange(0, 10)]
+    for ids in calls:
+        before = (mgr.cached_idx_map.clone(), mgr.inverted_cached_idx.clone(), mgr.freq_cnter.clone(),
+                  mgr._slot_epoch.clone(), mgr._dev_state.clone(), list(mgr.num_hits_history))
+        if ids.numel() == 30:                      # 30 new rows while 35 slots are occupied and 20 of them protected
+            with pytest.raises(AssertionError, match="increase cuda_row_num or decrease the training batch size"):
+                mgr.prepare_ids(ids.cuda())
+        elif int(ids.max()) >= N:
+            with pytest.raises(IndexError):
+                mgr.prepare_ids(ids.cuda())
+        else:
+            assert torch.equal(mgr.prepare_ids(ids.cuda()).cpu(), omgr.prepare_ids(ids))
+            assert_maps_equal(mgr, omgr)
+            continue
+        after = (mgr.cached_idx_map, mgr.inverted_cached_idx, mgr.freq_cnter, mgr._slot_epoch, mgr._dev_state)
+        for b, a in zip(before, after):
+            b[_lib_state_mask(b)] = 0
+            a = a.clone()
+            a[_lib_state_mask(a)] = 0
+            assert torch.equal(b, a)
+        assert before[5] == mgr.num_hits_history
+        assert int(mgr._miss_bitmap.abs().sum()) == 0 and int(mgr._hit_bitmap.abs().sum()) == 0
+    assert sum(mgr.num_write_back_history) > 0
+
+
+def _lib_state_mask(tensor):
+    """dev_state counts the calls the device has completed, rejected ones included: ignore that word."""
+    from cachedembedding_b200 import _lib
+    mask = torch.zeros_like(tensor, dtype=torch.bool)
+    if tensor.numel() == _lib.STATE_WORDS and tensor.dtype == torch.int64:
+        mask[_lib.STATE_CALLS] = True
+    return mask
+
+
+@pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
+@pytest.mark.parametrize("stage_rows,adagrad", [(0, False), (5, False), (0, True)])
+def test_reference_loop_with_async_copy_flag(strategy, stage_rows, adagrad):
+    """The reference's loop, unchanged (/root/reference/recsys/dlrm_main.py:245-279 with the flag of :121,354):
+    set_cache_mgr_async_copy(True); one prepare_ids over the concatenated window on the CURRENT stream; then P forward /
+    backward steps with cache_op off.  The row traffic runs on the manager's copy stream (victims parked in HBM, fill,
+    write-back under the following steps); slot ids, maps and counters stay bit-exact against the oracle, pooled sums
+    and the flushed table within 1e-5."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(21)
+    N, D, F, B, P = 5000, 128, 4, 48, 3
+    weight = torch.randn(N, D, generator=gen) * 0.01
+    freq = torch.randint(0, 100, (N,), generator=gen)
+    kw = dict(mode="sum", include_last_offset=True, sparse=True, cache_ratio=0.2, ids_freq_mapping=freq, warmup_ratio=0.7)
+    model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(ce.EvictionStrategy, strategy),
+                                  fused_optimizer="rowwise_adagrad" if adagrad else "sgd", lr=0.5, eps=1e-6, **kw)
+    omodel = OracleCachedEmbeddingBag(N, D, _weight=weight.clone(), evict_strategy=getattr(OStrategy, strategy), **kw)
+    model.set_cache_mgr_async_copy(True)
+    mgr, omgr = model.cache_weight_mgr, omodel.cache_weight_mgr
+    mgr.stage_rows = stage_rows
+    oopt = torch.optim.SGD(omodel.parameters(), lr=0.5)
+    offsets = torch.arange(F * B + 1)
+    state = np.zeros(N)
+    ref_w = weight.double().numpy().copy()
+    for k in range(7):
+        window = [(torch.rand(F * B, generator=gen) ** 2 * N).long().clamp_(0, N - 1) for _ in range(P)]
+        slots = mgr.prepare_ids(torch.cat([w.cuda() for w in window]))           # dlrm_main.py:259
+        oslots = omgr.prepare_ids(torch.cat(window))
+        assert torch.equal(slots.cpu(), oslots), f"slot ids differ in window {k}"
+        assert_maps_equal(mgr, omgr)
+        model.set_cache_op(False); omodel.set_cache_op(False)
+        for j, (s, os_) in enumerate(zip(torch.chunk(slots, P), torch.chunk(oslots, P))):
+            g = torch.randn(F * B, D, generator=gen)
+            out = model(s, offsets.cuda())
+            out.backward(g.cuda())
+            if adagrad:
+                want = torch.from_numpy(ref_w[omgr.idx_map[window[j]].numpy()]).float()
+                close(out.cpu(), want)
+                ref_w, state = rowwise_adagrad_reference(ref_w, state, omgr.idx_map[window[j]].numpy(), offsets.numpy(),
+                                                         g.double().numpy(), 0.5, 1e-6)
+            else:
+                oout = omodel(os_, offsets)
+                close(out.cpu(), oout.detach())
+                oout.backward(g)
+                oopt.step(); oopt.zero_grad()
+    assert sum(mgr.num_write_back_history) > 0 and mgr._own_copy_stream is not None
+    mgr.flush(); omgr.flush()
+    if adagrad:
+        close(mgr.weight, torch.from_numpy(ref_w).float())
+        close(mgr.row_state, torch.from_numpy(state).float())
+    else:
+        close(mgr.weight, omgr.weight)
+        assert_maps_equal(mgr, omgr)
 
 
 # ---------------------------------------------------------------------------------------------------- BASELINE configs
