@@ -16,8 +16,12 @@ for it; otherwise the rows are scaled down and `config.row_scale` says by how mu
 N > 1: the same tables sharded table-wise over the ranks (BASELINE.json configs[3]), global batch 65536 ("strong"
 scaling: total work is fixed); the all-to-all of pooled embeddings and of their gradients is fused into the forward /
 backward kernels over NVLink peer memory (--no-fused-exchange: NCCL all-to-all, the reference's way).
-By default the cache operation of window k+1 runs on side streams under the compute of window k (look-ahead driver,
---no-overlap for the reference's serial order).  `--impl reference` times the CPU oracle port on the host cores.
+By default the cache operation of window k+1 runs on side streams under the compute of window k (look-ahead driver:
+window k+1 is submitted right after the FIRST step of window k; --no-overlap for the reference's serial order).
+N > 1 first runs an untimed parity leg (bench_verify.py: fused NVLink exchange vs NCCL exchange bit for bit, slot maps,
+pooled sums and tables against the CPU oracle, table-wise and column-wise) and fails the run on a mismatch; the record
+is the line's `parity_check`.  `--parallelism column` times the column-wise bag instead of the table-wise one.
+`--impl reference` times the CPU oracle port on the host cores.
 """
 from __future__ import annotations
 
@@ -172,8 +176,24 @@ def run_b200(args):
         wl["cache_ratio"] = args.cache_ratio
     rows_all = list(wl["rows"])
     D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
-    # every rank's tables must fit the host: scale rows down only if they do not
+    column = args.parallelism == "column" and world > 1
     arrange = rank_arrange(rows_all, world, args.placement)
+
+    # ---- untimed parity leg (N > 1): the parallel bags against the CPU oracle on small tables ------------------------
+    parity = None
+    if world > 1 and not args.no_verify:
+        from bench_verify import verify_parallel
+        t0 = time.time()
+        parity = verify_parallel([300 + 37 * (t % 5) for t in range(len(rows_all))], arrange, D)
+        parity["seconds"] = round(time.time() - t0, 1)
+        if not parity["ok"] or args.verify_only:
+            if rank == 0:
+                print(json.dumps({"metric": "embedding lookups/sec (fwd+bwd)", "value": None, "n_gpus": world,
+                                  "parity_check": parity}))
+            dist.destroy_process_group()
+            sys.exit(0 if parity["ok"] else 1)
+
+    # every rank's tables must fit the host: scale rows down only if they do not
     need_gb = sum(rows_all) * D * 4 / 1e9
     avail_gb = host_mem_available_gb()
     row_scale = args.row_scale
@@ -182,7 +202,8 @@ def run_b200(args):
         while need_gb / row_scale > 0.8 * avail_gb and row_scale < 1024:
             row_scale *= 2
     rows_all = [max(1, r // row_scale) for r in rows_all]
-    my_tables = [t for t, r in enumerate(arrange) if r == rank]
+    # column-wise: every rank holds ALL rows (a D / W column slice of each) and looks up ALL ids of the global batch
+    my_tables = list(range(len(rows_all))) if column else [t for t, r in enumerate(arrange) if r == rank]
     rows_loc = [rows_all[t] for t in my_tables]
     F, F_loc = len(rows_all), len(my_tables)
     N_loc = sum(rows_loc)
@@ -192,12 +213,12 @@ def run_b200(args):
     # one look-ahead window of a 65536 batch touches (its own capacity assert fires); demand per rank is set by the
     # number of tables, not by their rows.
     total_slots = max(int(sum(wl["rows"]) * wl["cache_ratio"]), 1)
-    C_loc = min(N_loc, total_slots // world)
+    C_loc = min(N_loc, total_slots if column else total_slots // world)
     K, W = args.steps, args.warmup
     total_steps = W + K
-    windows = (total_steps + P - 1) // P + 1      # + the window the last timed one prefetches
+    windows = (total_steps + P - 1) // P + 2      # + the windows the last timed one prefetches
 
-    gen = torch.Generator(device=dev).manual_seed(SEED + rank)
+    gen = torch.Generator(device=dev).manual_seed(SEED + (0 if column else rank))
     rows_dev = torch.tensor(rows_loc, dtype=torch.long, device=dev)
 
     # id frequencies counted over a sample of the synthetic "dataset" (the reference counts its training set:
@@ -212,6 +233,9 @@ def run_b200(args):
                   lr=1.0)
     if world == 1:
         model = ce.CachedEmbeddingBag(N_loc, D, ids_freq_mapping=freq, **common)
+    elif column:
+        # the reference's default module (recsys/models/dlrm.py:70-81)
+        model = ce.ParallelCachedEmbeddingBag(N_loc, D, ids_freq_mapping=freq, **common)
     else:
         # the reference's table-wise module (recsys/models/dlrm.py:53-68): every table with its rank and frequencies
         table_freq = dict(zip(my_tables, torch.split(freq, rows_loc)))
@@ -233,40 +257,46 @@ def run_b200(args):
     # the gradient of the pooled embeddings, fixed (benchmark_cache.py:64); for N > 1 it is what the dense part
     # returns for this rank's slice of the batch, all features
     strides = split_sizes(B, world)
-    dim_per_rank = [D * sum(1 for r in arrange if r == q) for q in range(world)]
     if world > 1:
-        grad_full = torch.randn(strides[rank], F * D, device=dev)
+        grad_full = torch.randn(strides[rank], F, D, device=dev) if column else torch.randn(strides[rank], F * D, device=dev)
     else:
         grad_full = torch.randn(n_b, D, device=dev)
 
     grad_holder = {"g": grad_full}
     # one look-ahead driver for the whole run: its streams and plan buffers are warmed once
     prefetcher = {"pf": ce.LookaheadPrefetcher(model) if overlap else None}
+    col_hook = (lambda x: x.view(F, B, -1).transpose(0, 1)) if column else None     # recsys/models/dlrm.py:26-27
 
     def embed_step(slots):
-        out = model(slots, offsets)          # table-wise: (B / W, F * D) after the exchange; single GPU: (F * B, D)
+        # table-wise: (B / W, F * D) after the exchange; column-wise: (B / W, F, D); single GPU: (F * B, D)
+        out = model(slots, offsets, shape_hook=col_hook) if column else model(slots, offsets)
         out.backward(grad_holder["g"])
         return out
 
     class Runner:
-        """Steps of one arm, in order.  With the look-ahead driver the pipeline stays primed across calls: when the last
-        step of window w has been enqueued, window w+1 is submitted to the side streams -- also at the end of a call, so
-        the first window of the NEXT call (the timed one after the warm-up) was prepared under the previous window's
-        compute exactly as in steady state; every timed step still carries 1/P of one prepare_ids (for a later window)."""
+        """Steps of one arm, in order.  With the look-ahead driver, window w+1 is submitted to the side streams right
+        after the FIRST step of window w has been enqueued (prepare_ids never waits for the GPU, so this costs the host
+        a few dozen launches), i.e. every window's cache operation has the rest of the previous window to hide under,
+        wherever the timed region starts; every timed window still submits exactly one prepare_ids."""
 
         def __init__(self, batches, host_inputs, overlap=overlap):
             self.batches, self.host, self.overlap = batches, host_inputs, overlap
-            self.w, self.slots, self.next_w, self.next = -1, None, -1, None
+            self.w, self.slots, self.handles, self.h2d = -1, None, {}, 0
             self.plan = dict(offsets=offsets) if not args.no_plan_side else {}
 
         def ids(self, w):
             return self.batches[w * P:(w + 1) * P]
 
+        def submit(self, w):
+            if w not in self.handles and (w + 1) * P <= len(self.batches):
+                self.handles[w] = prefetcher["pf"].submit(self.ids(w), **self.plan)
+                self.h2d += P * n_b * 8 if self.host else 0
+
         def run(self, first, count):
             """Steps [first, first+count).  host inputs: ids start in pinned host memory and are copied H2D inside the
             region (every batch of a window before its prepare_ids, like recsys/dlrm_main.py:248-259); one pooled row
             is read back D2H per step."""
-            h2d = d2h = 0
+            self.h2d = d2h = 0
             pf = prefetcher["pf"] if self.overlap else None
             saved_protect = mgr.protect_windows
             if not self.overlap:
@@ -275,29 +305,28 @@ def run_b200(args):
                 w, j = divmod(s, P)
                 if w != self.w:                  # entering a new window
                     if self.overlap:
-                        if self.next_w != w:
-                            self.next, self.next_w = pf.submit(self.ids(w), **self.plan), w
-                            h2d += P * n_b * 8 if self.host else 0
-                        self.slots = torch.chunk(self.next.wait(), P)
+                        self.submit(w)           # only the very first window of an arm is not in flight already
+                        self.slots = torch.chunk(self.handles.pop(w).wait(), P)
                     else:
                         win = torch.cat([b.to(dev, non_blocking=True) for b in self.ids(w)])
-                        h2d += P * n_b * 8 if self.host else 0
+                        self.h2d += P * n_b * 8 if self.host else 0
                         self.slots = torch.chunk(mgr.prepare_ids(win), P)
                     self.w = w
                 out = embed_step(self.slots[j])
                 if self.host:
                     result_host.copy_(out.view(-1)[:D], non_blocking=True)
                     d2h += D * 4
-                if self.overlap and j == P - 1 and (w + 1) * P < len(self.batches):
+                if self.overlap and j == 0:
+                    self.submit(w + 1)
+                if self.overlap and j == P - 1:
                     pf.window_enqueued()
-                    self.next, self.next_w = pf.submit(self.ids(w + 1), **self.plan), w + 1
-                    h2d += P * n_b * 8 if self.host else 0
             mgr.protect_windows = saved_protect
-            return h2d, d2h
+            return self.h2d, d2h
 
         def finish(self):
             if self.overlap:
                 prefetcher["pf"].drain()
+                self.handles.clear()
 
     def timed(runner, first, count):
         if world > 1:
@@ -374,32 +403,61 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     uniq = [int(torch.unique(b).numel()) for b in arms["profile"][W:W + min(K, 8)]]
     u_avg = sum(uniq) / len(uniq)
-    alg = {   # algorithmic bytes per launch
-        "bag_forward": n_b * (8 + 4 * D) + n_b * 4 * D + (n_b + 1) * 8,
-        "bag_backward_phase1": n_b * 4 * D + u_avg * 8 * D + n_b * 8,
+    row_b = 4 * (D // world if column else D)
+    # Bytes per launch.  "compulsory": what DRAM has to move at least -- ids, offsets, every UNIQUE
+    # row once (a batch re-reads its hot rows from the 126 MB L2), every output / gradient row once.  "algorithmic":
+    # SURVEY.md section 8d's per-lookup figure, which charges a full row read to every lookup.
+    compulsory = {
+        "bag_forward": n_b * 8 + (n_b + 1) * 8 + u_avg * row_b + n_b * row_b,
+        "bag_backward_phase1": n_b * row_b + n_b * 8 + u_avg * 2 * row_b,
+    }
+    alg = {
+        "bag_forward": n_b * (8 + row_b) + n_b * row_b + (n_b + 1) * 8,
+        "bag_backward_phase1": n_b * row_b + u_avg * 2 * row_b + n_b * 8,
     }
     kernels = {}
     for name, (ms, cnt) in prof.items():
         kernels[name] = {"ms_per_step": ms / K, "launch_groups": cnt}
         if name in alg and cnt:
-            kernels[name]["achieved_gbs"] = alg[name] / (ms / cnt / 1e3) / 1e9
+            kernels[name]["us_per_launch"] = ms / cnt * 1e3
+            kernels[name]["compulsory_gbs"] = compulsory[name] / (ms / cnt / 1e3) / 1e9
+            kernels[name]["algorithmic_gbs"] = alg[name] / (ms / cnt / 1e3) / 1e9
+    kernels["swap_rows"] = {"ms_per_step": sum(kernels.get(k, {}).get("ms_per_step", 0.0)
+                                               for k in ("fill_rows", "write_back", "park_victims")),
+                            "note": "fill_rows + write_back + park_victims"}
     dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_step"])
-    achieved = kernels[dom]["achieved_gbs"]
-    # DRAM traffic per launch from the committed `ncu --set full` capture of the same launch shape
-    # (profiles/r1b_fwd_bwd_sort.summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); only for that shape
-    ncu_traffic = {"bag_forward": 911.0e6, "bag_backward_phase1": 968.0e6} if (
-        args.workload == "criteo1tb" and world == 1) else {}
-    traffic = ncu_traffic.get(dom)
+    achieved = kernels[dom]["compulsory_gbs"]
+    # DRAM traffic per launch of that kernel from an `ncu --set full` capture of this launch shape, if one has been
+    # recorded with scripts/ncu_traffic.sh (profiles/ncu_traffic.json); never a constant in this file
+    traffic = None
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(traffic_path):
+        rec = json.load(open(traffic_path)).get(f"{args.workload}:n{world}:{args.parallelism}", {})
+        traffic = rec.get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": int(compulsory[dom]),
+                "basis": ("compulsory DRAM bytes per launch (ids + offsets + unique rows + output / gradient rows) / the "
+                          "kernel's CUDA-event time in this run, each kernel alone on the GPU"),
+                "algorithmic_frac": round(kernels[dom]["algorithmic_gbs"] / peak, 4),
                 "algorithmic_bytes_per_launch": int(alg[dom]),
-                "note": ("algorithmic bytes count every looked-up row (n x 4D); a batch has only ~%d unique rows, which "
-                         "stay in the 126 MB L2, so DRAM sees mostly the output write: a fraction above 1 is L2 reuse, "
-                         "not skipped work" % round(u_avg))}
-    if traffic:
-        roofline["dram_gbs"] = round(traffic / (kernels[dom]["ms_per_step"] * K / kernels[dom]["launch_groups"] / 1e3) / 1e9, 1)
-        roofline["dram_frac"] = round(roofline["dram_gbs"] / peak, 4)
+                "note": ("algorithmic bytes charge a row read to every lookup (SURVEY.md 8d); a batch has only ~%d unique "
+                         "rows and re-reads them from L2, so algorithmic_frac can exceed 1 -- frac is the honest one"
+                         % round(u_avg))}
+    # whole step against the HBM roofline: compulsory bytes of forward + backward + the sort / probe traffic
+    step_bytes = compulsory["bag_forward"] + compulsory["bag_backward_phase1"] + n_b * 40 + n_b * 20
+    roofline["step_hbm_frac"] = round(step_bytes / (ms_total / K / 1e3) / 1e9 / peak, 4)
 
+    if world > 1:     # every rank's kernel times: the step is the max over ranks
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: round(v["ms_per_step"], 4) for k, v in kernels.items()})
+        for k in kernels:
+            kernels[k]["ms_per_step_by_rank"] = [g.get(k) for g in gathered]
+
+    par = "single GPU" if world == 1 else (
+        f"column-wise x{world} (D / W columns per rank, every rank looks up all ids), NCCL all-to-all of pooled embeddings"
+        if column else f"table-wise x{world}, pooled-embedding all-to-all " +
+        ("via NCCL" if args.no_fused_exchange else "fused into the fwd/bwd kernels over NVLink peer memory"))
     line = {
         "metric": "embedding lookups/sec (fwd+bwd)", "value": value, "unit": "lookups/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
@@ -407,15 +465,13 @@ def run_b200(args):
         "config": {
             "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
                         f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
-            "lookahead": ("prepare_ids(window k+1) on side streams under window k; the pipeline stays primed across the "
-                          "warm-up/timed boundary (each timed step carries 1/P of one prepare_ids)") if overlap
-            else "serial (reference order)",
-            "tables_per_rank": [sum(1 for a in arrange if a == q) for q in range(world)],
-            "row_scale": row_scale, "host_table_gb": round(N_loc * D * 4 / 1e9, 2), "cache_rows_per_rank": C_loc,
+            "lookahead": ("prepare_ids(window k+1) is enqueued on side streams right after the first step of window k "
+                          "(no host wait inside prepare_ids); each timed window submits one prepare_ids, wherever the "
+                          "timed region starts") if overlap else "serial (reference order)",
+            "tables_per_rank": [F] * world if column else [sum(1 for a in arrange if a == q) for q in range(world)],
+            "row_scale": row_scale, "host_table_gb": round(N_loc * row_b / 1e9, 2), "cache_rows_per_rank": C_loc,
             "ids": f"per-table power law s={SKEW} (reference generator), seed {SEED}",
-            "parallelism": "single GPU" if world == 1 else (
-                f"table-wise x{world}, pooled-embedding all-to-all " +
-                ("via NCCL" if args.no_fused_exchange else "fused into the fwd/bwd kernels over NVLink peer memory")),
+            "parallelism": par,
             "l2": "inputs larger than L2: each step streams >= 2 x n_b x 512 B (1.7 GB at n_b = 1.7 M) vs 126 MB L2",
             "unique_rows_per_step": round(u_avg), "unique_hits": hit_u, "unique_misses": miss_u, "evicted_rows": evicted,
             "miss_ratio_lookups": round(miss_ratio_lookups, 5), "setup_s": round(setup_s, 1),
@@ -423,10 +479,16 @@ def run_b200(args):
         "roofline": roofline,
         "kernels": kernels,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K,
+                "note": ("ids of every batch come from pinned host memory inside the timed region; the pooled embeddings "
+                         "stay in HBM by design (their consumer is the dense part of the model), one pooled row per step "
+                         "is read back as the result; the D2H traffic that matters -- evicted rows going back to the "
+                         "host table -- is inside the region in both arms")},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity_check"] = parity
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_oracle_arm(args.workload, steps=P, warmup=0, budget_s=40.0)["cpu_baseline"]
     if rank == 0:
@@ -533,6 +595,10 @@ def main():
                     help="auto: the reference's table->rank map where it has one, else the snake; snake: always")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: NCCL all-to-all instead of peer-memory kernels")
     ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
+    ap.add_argument("--parallelism", default="table", choices=["table", "column"],
+                    help="N > 1: table-wise sharding (BASELINE.json configs[3]) or the reference's default column-wise bag")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the untimed parity leg")
+    ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:

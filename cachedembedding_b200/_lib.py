@@ -54,7 +54,7 @@ class Table(Structure):
         ("protect_windows", c_int32),
         ("host_table", c_void_p), ("host_state", c_void_p), ("cache", c_void_p), ("cache_state", c_void_p),
         ("idx_map", c_void_p), ("row2slot", c_void_p), ("slot2row", c_void_p), ("freq", c_void_p),
-        ("slot_epoch", c_void_p), ("miss_bitmap", c_void_p), ("hit_bitmap", c_void_p), ("dev_state", c_void_p),
+        ("slot_epoch", c_void_p), ("miss_bitmap", c_void_p), ("hit_flags", c_void_p), ("dev_state", c_void_p),
     ]
 
 

@@ -130,7 +130,7 @@ class CachedParamMgr(nn.Module):
             self.row_state = None
             self._state_pin = None
             self.cuda_cached_state = None
-        self.register_buffer("_hit_bitmap", torch.zeros((C + 31) // 32, dtype=torch.int32, device=dev),
+        self.register_buffer("_hit_flags", torch.zeros((C + 15) // 16 * 16, dtype=torch.uint8, device=dev),
                              persistent=False)
         state = torch.zeros(_lib.STATE_WORDS, dtype=torch.int64)
         state[_lib.STATE_AVAIL] = C
@@ -182,7 +182,7 @@ class CachedParamMgr(nn.Module):
         t.freq = self._freq.data_ptr() if self._freq is not None else None
         t.slot_epoch = self._slot_epoch.data_ptr()
         t.miss_bitmap = self._miss_bitmap.data_ptr()
-        t.hit_bitmap = self._hit_bitmap.data_ptr()
+        t.hit_flags = self._hit_flags.data_ptr()
         t.dev_state = self._dev_state.data_ptr()
         return t
 

@@ -10,24 +10,19 @@ import torch
 import torch.distributed as dist
 
 
-def get_partition(embedding_dim: int, rank: int, world_size: int):
-    """Column range [start, end) of `rank` under the torch.tensor_split rule (reference: recsys/utils/misc.py:138-154)."""
-    if world_size == 1:
-        return 0, embedding_dim, True
-    assert embedding_dim >= world_size, \
-        f"Embedding dimension {embedding_dim} must be larger than the world size {world_size} of the process group"
-    chunk_size = embedding_dim // world_size
-    threshold = embedding_dim % world_size
-    if threshold == 0:
-        return rank * chunk_size, (rank + 1) * chunk_size, True
-    size_list = [chunk_size + 1 if i < threshold else chunk_size for i in range(world_size)]
-    offset = sum(size_list[:rank])
-    return offset, offset + size_list[rank], False
-
-
 def split_sizes(total: int, world_size: int) -> List[int]:
     """torch.tensor_split sizes: the first `total % W` parts get one extra."""
     return [total // world_size + int(i < total % world_size) for i in range(world_size)]
+
+
+def get_partition(embedding_dim: int, rank: int, world_size: int):
+    """(start, end, divides_evenly): the columns of `rank` when D columns are dealt out by the torch.tensor_split rule
+    (what the reference's recsys/utils/misc.py:138-154 computes for the column-wise bag)."""
+    if world_size > 1 and embedding_dim < world_size:
+        raise AssertionError(f"cannot split {embedding_dim} embedding columns over {world_size} ranks")
+    widths = split_sizes(embedding_dim, world_size)
+    start = sum(widths[:rank])
+    return start, start + widths[rank], embedding_dim % world_size == 0
 
 
 def exchange(recv: List[torch.Tensor], send: List[torch.Tensor], group=None):

@@ -5,9 +5,10 @@
 // with CPU gather/scatter + staged memcpys and synchronises the device 8+ times per call.  Here one call ENQUEUES a
 // fixed sequence of kernels and never waits for the GPU: every count (misses M, evictions E, free slots) stays in
 // device memory, grids are upper bounds, and the state-changing kernels are gated by a device-side verdict.
-//   * probe       : one pass over the ids.  Resident rows answer from the dense int32 row->slot map and set their
-//                   slot's bit in a hit bitmap (first setter counts the unique hit); missing rows set a bit in a per-row
-//                   bitmap and append their position to a fix-up list.  No sort.
+//   * probe       : one pass over the ids.  Resident rows answer from the dense int32 row->slot map and raise their
+//                   slot's hit flag (a plain byte store: no atomics on the hit path; the unique hits are counted from
+//                   the flags afterwards); missing rows set a bit in a per-row bitmap and append their position to a
+//                   fix-up list.  No sort.
 //   * rank        : popcount-scan of the row bitmap emits the missed rows in ascending row order (the reference's
 //                   sorted-unique contract) and their count M.
 //   * decide      : one thread applies the A.3 capacity assert and the id-range check, fixes E = max(0, M - free).
@@ -49,6 +50,8 @@ struct SelectState {             // radix-select of the k smallest keys
     long long k;                 // how many of the keys that match `prefix` are still to be taken
     int hist[256];
 };
+
+__device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ int32_t row_of_id(const cebag_table& t, int64_t id) {
     return t.idx_map ? __ldg(t.idx_map + id) : (int32_t)id;
@@ -128,7 +131,6 @@ __global__ void __launch_bounds__(kThreads)
 probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, int64_t* __restrict__ out,
              int32_t* __restrict__ miss_pos, int32_t* __restrict__ counters) {
     const int lane = lane_id();
-    int32_t uniq = 0;
     const int64_t tile = (int64_t)kThreads * kProbeIds;
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
         int64_t id[kProbeIds];
@@ -155,10 +157,9 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
             bool miss = live[u] && slot[u] < 0;
             if (live[u] && !miss) {
                 out[i] = slot[u];
-                // the slot is needed by this call: the first id to say so counts the unique hit
-                const uint32_t bit = 1u << (slot[u] & 31);
-                uint32_t* word = t.hit_bitmap + (slot[u] >> 5);
-                if (!(*reinterpret_cast<volatile uint32_t*>(word) & bit)) uniq += !(atomicOr(word, bit) & bit);
+                // the slot is needed by this call (racing stores of the same 1 are fine)
+                uint8_t* flag = t.hit_flags + slot[u];
+                if (!*reinterpret_cast<volatile uint8_t*>(flag)) *flag = 1;
             }
             // warp-aggregated append of the positions that missed
             unsigned m = __ballot_sync(0xffffffffu, miss);
@@ -176,9 +177,21 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
             }
         }
     }
+}
+
+// unique hits of the call = raised hit flags (16 slots per 128-bit load; the flag array is padded to 16)
+__global__ void __launch_bounds__(kThreads)
+count_hits_kernel(const cebag_table t, int32_t* __restrict__ counters) {
+    const int64_t vecs = ceil_div_dev(t.cache_rows, 16);
+    const uint4* flags = reinterpret_cast<const uint4*>(t.hit_flags);
+    int32_t c = 0;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < vecs; v += (int64_t)gridDim.x * kThreads) {
+        const uint4 f = flags[v];
+        c += __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w);     // flags are 0 or 1
+    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, d);
-    if (lane == 0 && uniq) atomicAdd(&counters[kCtrUniqueHits], uniq);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane_id() == 0 && c) atomicAdd(&counters[kCtrUniqueHits], c);
 }
 
 // ---- bitmap ranking: rows in ascending order -----------------------------------------------------------------------
@@ -236,7 +249,7 @@ bitmap_emit_kernel(const uint32_t* __restrict__ bitmap, int64_t words, const int
 __device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, int32_t epoch, unsigned long long* key) {
     int32_t row = t.slot2row[s];
     if (row < 0) return false;                                                  // empty
-    if ((t.hit_bitmap[s >> 5] >> (s & 31)) & 1u) return false;                   // needed by this call
+    if (t.hit_flags[s]) return false;                                            // needed by this call
     const int32_t stamp = t.slot_epoch[s];
     if (stamp != 0 && epoch - stamp < t.protect_windows) return false;          // needed by a protected window
     if (t.strategy == CEBAG_EVICT_LFU) *key = (unsigned long long)t.freq[s];    // smallest counter first
@@ -365,21 +378,20 @@ commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ counter
     }
 }
 
-// slots hit by this call get the window stamp (only if the call was accepted); the hit bitmap is all-zero again
+// slots hit by this call get the window stamp (only if the call was accepted); the hit flags are all-zero again
 __global__ void __launch_bounds__(kThreads)
 stamp_hits_kernel(const cebag_table t, const int32_t* __restrict__ counters, int64_t words) {
     const bool ok = counters[kCtrStatus] == CEBAG_OK;
     const int32_t epoch = counters[kCtrEpoch];
+    uint32_t* flags4 = reinterpret_cast<uint32_t*>(t.hit_flags);          // 4 slots per word
     for (int64_t w = (int64_t)blockIdx.x * kThreads + threadIdx.x; w < words; w += (int64_t)gridDim.x * kThreads) {
-        uint32_t bits = t.hit_bitmap[w];
-        if (!bits) continue;
-        t.hit_bitmap[w] = 0u;
+        const uint32_t f = flags4[w];
+        if (!f) continue;
+        flags4[w] = 0u;
         if (!ok) continue;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            t.slot_epoch[w * 32 + b] = epoch;
-        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((f >> (8 * b)) & 0xffu) t.slot_epoch[w * 4 + b] = epoch;
     }
 }
 
@@ -605,7 +617,7 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     int64_t nn = n > 0 ? n : 1;
     int64_t C = t->cache_rows;
     L.words = ceil_div(t->num_rows, 32);
-    L.hit_words = ceil_div(C, 32);
+    L.hit_words = ceil_div(C, 16) * 4;              // the hit flags as 32-bit words (4 slots each)
     L.bitmap_blocks = ceil_div(L.words, kWordsPerBlock);
     size_t off = 0;
     L.counters = off; off += align(kNumCounters * 4);
@@ -633,7 +645,8 @@ int check_table(const cebag_table* t) {
     CEBAG_REQUIRE(t->dim > 0 && t->cache_rows > 0, "dim / cache_rows");
     CEBAG_REQUIRE(t->strategy == CEBAG_EVICT_LFU || t->strategy == CEBAG_EVICT_DATASET, "strategy");
     CEBAG_REQUIRE(t->host_table && t->cache && t->row2slot && t->slot2row && t->slot_epoch && t->miss_bitmap &&
-                  t->hit_bitmap && t->dev_state, "table pointers");
+                  t->hit_flags && t->dev_state, "table pointers");
+    CEBAG_REQUIRE(aligned16(t->hit_flags), "hit_flags alignment");
     CEBAG_REQUIRE(t->strategy != CEBAG_EVICT_LFU || t->freq != nullptr, "LFU needs freq");
     CEBAG_REQUIRE(t->protect_windows >= 1 && t->protect_windows <= 1024, "protect_windows");
     return CEBAG_OK;
@@ -732,10 +745,11 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
     const bool lfu = t->strategy == CEBAG_EVICT_LFU;
 
     {
-        KernelScope scope(kKernProbe, stream, 2);
+        KernelScope scope(kKernProbe, stream, 3);
         begin_call_kernel<<<1, 32, 0, stream>>>(*t, counters);
         probe_kernel<<<grid_for(ceil_div(n, kProbeIds), kThreads, 8), kThreads, 0, stream>>>(*t, ids, n, slot_ids_out,
                                                                                             miss_pos, counters);
+        count_hits_kernel<<<grid_for(ceil_div(C, 16), kThreads, 8), kThreads, 0, stream>>>(*t, counters);
         CEBAG_LAUNCH_CHECK();
     }
     {   // missed rows, ascending: count, then (after the verdict) emit

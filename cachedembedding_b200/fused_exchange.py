@@ -98,6 +98,7 @@ class FusedExchange:
         self.out_buf = PeerBuffer(rows_max * self.F * self.D, group)
         self.grad_buf = PeerBuffer(rows_max * self.F * self.D, group)
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        self._forward_pending = False      # a forward whose backward has not run yet
         self._xo = self._struct(self.out_buf)
         self._xg = self._struct(self.grad_buf)
 
@@ -139,6 +140,9 @@ class _FusedTablewiseFunction(torch.autograd.Function):
         a = _bag_args(weight, slot_ids, offsets, None, bag.include_last_offset, _lib.MODE_SUM, bag.padding_idx,
                       _lib.LAYOUT_EXCHANGE, exch.B)
         a.exchange = ctypes.pointer(exch._xo)
+        if exch._forward_pending:
+            exch.barrier()                  # two forwards in a row: peers may still be reading the previous output
+        exch._forward_pending = True
         _lib.check(lib.cebag_bag_forward(ctypes.byref(a), None, _stream_ptr()))
         exch.barrier()                      # every rank's rows have landed in my buffer
         ctx.save_for_backward(weight, slot_ids, offsets)
@@ -151,6 +155,7 @@ class _FusedTablewiseFunction(torch.autograd.Function):
         lib = _lib.load()
         weight, slot_ids, offsets = ctx.saved_tensors
         bag, exch = ctx.bag, ctx.exch
+        exch._forward_pending = False
         fused = bag._fused_optimizer
         gbuf = exch.grad_tensor()
         if grad_out.data_ptr() != gbuf.data_ptr():

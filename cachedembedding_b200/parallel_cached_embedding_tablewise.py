@@ -117,24 +117,34 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         """Fold the pooled-embedding all-to-all (and its backward) into the gather / optimizer kernels.  Needs the fused
         optimizer (`set_fused_optimizer`), mode 'sum', no per-sample weights and more than one rank."""
         self._fused_exchange_on = bool(flag)
-        if not flag and getattr(self, "_exchange", None) is not None:
-            self._exchange.close()
+        if not flag:
+            for exch in getattr(self, "_exchanges", {}).values():
+                exch.close()
+            self._exchanges = {}
             self._exchange = None
 
     def _use_fused_exchange(self, batch_size, per_sample_weights) -> bool:
+        """The fused exchange hands out a view of a persistent peer buffer that the NEXT forward overwrites, and it is
+        the backward's barrier that keeps a fast rank from doing so while a peer still reads: it is used for training
+        steps only (grad enabled, module in training mode); evaluation takes the NCCL path, whose outputs are fresh
+        tensors."""
         return (getattr(self, "_fused_exchange_on", False) and self.world_size > 1 and per_sample_weights is None
-                and self.mode == "sum" and self._fused_optimizer is not None and batch_size >= self.world_size)
+                and self.mode == "sum" and self._fused_optimizer is not None and batch_size >= self.world_size
+                and self.training and torch.is_grad_enabled())
 
     def _forward_fused(self, slot_ids, offsets, batch_size):
         from .fused_exchange import FusedExchange, _FusedTablewiseFunction
-        exch = getattr(self, "_exchange", None)
-        if exch is None or exch.B != batch_size:
-            if exch is not None:
-                exch.close()
+        if not hasattr(self, "_exchanges"):
+            self._exchanges = {}
+        exch = self._exchanges.get(batch_size)
+        if exch is None:
+            # one set of peer buffers per batch size, kept until enable_fused_exchange(False): outputs handed out
+            # earlier alias them, so a change of batch size must not free them
             total_features = len(self.rank_of_tables)
             feature_offset = sum(1 for r in self.rank_of_tables if r < self.rank)
             exch = FusedExchange(batch_size, total_features, feature_offset, self.embedding_dim, self.process_group)
-            self._exchange = exch
+            self._exchanges[batch_size] = exch
+        self._exchange = exch
         offsets = offsets.to(slot_ids.device)
         if offsets.dtype not in (torch.int32, torch.int64):
             offsets = offsets.long()

@@ -55,7 +55,7 @@ enum { CEBAG_LAYOUT_BAG_MAJOR = 0,     /* out[g, :]                       -- wha
  *   weight -> host_table, cuda_cached_weight -> cache, idx_map, cached_idx_map -> slot2row,
  *   inverted_cached_idx -> row2slot, freq_cnter -> freq.
  * B200-first differences: the id maps are int32 (half the HBM of the reference's int64 maps, which were 76 % of
- * its footprint); idx_map may be NULL (identity); a per-slot window stamp, a per-slot hit bitmap
+ * its footprint); idx_map may be NULL (identity); a per-slot window stamp, a per-slot hit flag
  * and a per-row miss bitmap replace the reference's sort-based unique/isin; the free-slot count and the window stamp
  * live in DEVICE memory (dev_state), so that prepare_ids never has to wait for the GPU.
  */
@@ -83,7 +83,7 @@ typedef struct cebag_table {
     int64_t*  freq;           /* int64[C]   LFU counters (CEBAG_FREQ_EMPTY = empty); NULL for DATASET     */
     int32_t*  slot_epoch;     /* int32[C]   stamp of the last prepare_ids window that used the slot       */
     uint32_t* miss_bitmap;    /* uint32[ceil(N/32)] all-zero between calls                                */
-    uint32_t* hit_bitmap;     /* uint32[ceil(C/32)] all-zero between calls                                */
+    uint8_t*  hit_flags;      /* uint8[16 * ceil(C/16)] all-zero between calls: slots hit by the call     */
     int64_t*  dev_state;      /* int64[CEBAG_STATE_WORDS] HBM; [AVAIL] = C and the rest 0 for an empty cache */
 } cebag_table;
 

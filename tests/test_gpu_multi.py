@@ -216,3 +216,30 @@ def test_parallel_bags_two_ranks(worker):
     results = mgr.dict()
     mp.spawn(worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert all(results.get(r, False) for r in range(world)), dict(results)
+
+
+def _verify_leg_worker(rank, world, port, results):
+    """bench.py's untimed parity leg (bench_verify.verify_parallel) on the Criteo-1TB table placement for `world`."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import bench
+    from bench_verify import verify_parallel
+    arrange = bench.rank_arrange(bench.CRITEO_1TB_ROWS, world)
+    rec = verify_parallel([300 + 37 * (t % 5) for t in range(26)], arrange, 128)
+    results[rank] = rec
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_parity_leg_two_ranks():
+    _need_two_gpus()
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_verify_leg_worker, args=(world, port, results), nprocs=world, join=True)
+    for r in range(world):
+        assert results[r]["ok"], dict(results[r])
+        assert results[r]["tablewise"]["evicted_rows_this_rank"] > 0
+

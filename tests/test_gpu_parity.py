@@ -576,7 +576,7 @@ def test_rejected_call_leaves_no_trace_with_two_window_protection():
             a[_lib_state_mask(a)] = 0
             assert torch.equal(b, a)
         assert before[5] == mgr.num_hits_history
-        assert int(mgr._miss_bitmap.abs().sum()) == 0 and int(mgr._hit_bitmap.abs().sum()) == 0
+        assert int(mgr._miss_bitmap.abs().sum()) == 0 and int(mgr._hit_flags.sum()) == 0
     assert sum(mgr.num_write_back_history) > 0
 
 
