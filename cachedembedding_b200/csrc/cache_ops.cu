@@ -155,11 +155,15 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
         for (int u = 0; u < kProbeIds; ++u) {
             int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
             bool miss = live[u] && slot[u] < 0;
-            if (live[u] && !miss) {
-                out[i] = slot[u];
-                // the slot is needed by this call (racing stores of the same 1 are fine)
+            const bool hit = live[u] && !miss;
+            if (hit) out[i] = slot[u];
+            // The slot is needed by this call.  Ids arrive feature-major: the 32 ids of a warp belong to one table, and
+            // for the small tables most of them are the same few rows -- one lane per distinct slot raises the flag
+            // (racing stores of the same 1 are fine; the check may read a stale 0 from L1, which only costs a store).
+            const unsigned same = __match_any_sync(0xffffffffu, hit ? slot[u] : -1 - lane);
+            if (hit && lane == __ffs(same) - 1) {
                 uint8_t* flag = t.hit_flags + slot[u];
-                if (!*reinterpret_cast<volatile uint8_t*>(flag)) *flag = 1;
+                if (!*flag) *flag = 1;
             }
             // warp-aggregated append of the positions that missed
             unsigned m = __ballot_sync(0xffffffffu, miss);
