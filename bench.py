@@ -91,19 +91,10 @@ def host_mem_available_gb():
 
 
 def sample_ids(rows_dev, batch, gen, device):
-    """One batch of KJT-ordered global ids: values[f*B + b], one id per (feature, sample).
-
-    Per table the reference generator's long tail: idx = floor(u^(-1/s)) - 1, u ~ U[(1/N_f)^s, 1] in float64
-    (/root/reference/baselines/data/custom.py:76,89-91), made global by adding the table's row offset
-    (/root/reference/recsys/datasets/criteo.py:118-119)."""
-    F = rows_dev.numel()
-    n_f = rows_dev.to(torch.float64).view(F, 1)
-    lo = (1.0 / n_f) ** SKEW
-    u = torch.rand(F, batch, dtype=torch.float64, device=device, generator=gen) * (1.0 - lo) + lo
-    idx = torch.floor(u ** (-1.0 / SKEW)).long() - 1
-    idx = torch.minimum(idx.clamp_(min=0), rows_dev.view(F, 1) - 1)
-    offsets = torch.cumsum(rows_dev, 0) - rows_dev
-    return (idx + offsets.view(F, 1)).view(-1)
+    """One batch of KJT-ordered global ids: values[f*B + b], one id per (feature, sample), per table the reference
+    generator's long tail (cachedembedding_b200/synth_criteo.py; /root/reference/baselines/data/custom.py:76,89-91)."""
+    from cachedembedding_b200.synth_criteo import sample_ids as _sample
+    return _sample(rows_dev, batch, gen, device, SKEW)
 
 
 class ClockSampler:
@@ -224,10 +215,11 @@ def run_b200(args):
     # id frequencies counted over a sample of the synthetic "dataset" (the reference counts its training set:
     # /root/reference/recsys/datasets/feature_counter.py:21-29) -> LFU warm start
     t0 = time.time()
-    freq = torch.zeros(N_loc, dtype=torch.long, device=dev)
+    counter = ce.IdFrequencyCounter(N_loc, dev)          # GPU histogram kernel (cebag_id_histogram)
     for _ in range(args.freq_batches):
-        ids = sample_ids(rows_dev, B, gen, dev)
-        freq += torch.bincount(ids, minlength=N_loc)
+        counter.update(sample_ids(rows_dev, B, gen, dev))
+    freq = counter.result()
+    del counter
     common = dict(sparse=True, mode="sum", include_last_offset=True, cache_ratio=wl["cache_ratio"], warmup_ratio=0.7,
                   evict_strategy=ce.EvictionStrategy.LFU, cuda_row_num=C_loc, init_seed=SEED, fused_optimizer="sgd",
                   lr=1.0)

@@ -14,10 +14,13 @@ from .parallel_cached_embedding_tablewise import ParallelCachedEmbeddingBagTable
 from .lookahead import LookaheadPrefetcher, PrefetchHandle
 from .fused_exchange import FusedExchange, PeerBuffer
 from .collectives import dual_all_to_all, dual_all_to_all_tablewise, get_partition
+from .kjt_exchange import FusedKJTAllToAll
+from .synth_criteo import IdFrequencyCounter, SyntheticCriteo, write_kaggle_format
 
 __all__ = [
     'EvictionStrategy', 'TablewiseEmbeddingBagConfig', 'LimitBuffIndexCopyer', 'CachedParamMgr', 'CacheCapacityError',
     'CachedEmbeddingBag', 'FreqAwareEmbeddingBag', 'BaseEmbeddingBag', 'embedding_bag_cached', 'alloc_pinned_table',
     'ParallelCachedEmbeddingBag', 'ParallelCachedEmbeddingBagTablewise', 'dual_all_to_all',
-    'dual_all_to_all_tablewise', 'get_partition', 'LookaheadPrefetcher', 'PrefetchHandle',
+    'dual_all_to_all_tablewise', 'get_partition', 'LookaheadPrefetcher', 'PrefetchHandle', 'FusedKJTAllToAll',
+    'IdFrequencyCounter', 'SyntheticCriteo', 'write_kaggle_format',
 ]

@@ -31,7 +31,7 @@ EXPORTS = (
     "cebag_launch_count", "cebag_profile_enable", "cebag_profile_num_kernels", "cebag_profile_kernel_name",
     "cebag_profile_collect",
     "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
-    "cebag_host_device_pointer", "cebag_fill_uniform",
+    "cebag_host_device_pointer", "cebag_fill_uniform", "cebag_id_histogram",
     "cebag_device_alloc", "cebag_device_free", "cebag_ipc_export", "cebag_ipc_import", "cebag_ipc_close",
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_prepare_ids_async", "cebag_prepare_result_status",
     "cebag_flush", "cebag_preload", "cebag_admit_row", "cebag_evict_slot", "cebag_available_rows",
@@ -115,6 +115,7 @@ def _declare(lib):
     lib.cebag_host_unregister.argtypes = [c_void_p]
     lib.cebag_host_device_pointer.argtypes = [c_void_p, POINTER(c_void_p)]
     lib.cebag_fill_uniform.argtypes = [c_void_p, c_int64, c_float, c_float, c_uint64, c_void_p]
+    lib.cebag_id_histogram.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
     lib.cebag_device_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     lib.cebag_device_free.argtypes = [c_void_p]
     lib.cebag_ipc_export.argtypes = [c_void_p, ctypes.c_char_p]

@@ -10,7 +10,7 @@ namespace {
 const char* const kNames[kKernCount] = {
     "bag_forward", "bag_of", "radix_sort", "bag_backward_phase1", "bag_backward_phase2", "bag_backward_coo",
     "bag_backward_weights", "probe", "bitmap_rank", "victim_select", "free_slots", "victim_rank", "park_victims",
-    "fill_rows", "write_back", "fixup", "lfu_count", "flush", "move_rows", "fill_uniform"};
+    "fill_rows", "write_back", "fixup", "lfu_count", "flush", "move_rows", "fill_uniform", "id_histogram"};
 
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_enabled{0};

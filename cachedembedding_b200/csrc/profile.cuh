@@ -8,7 +8,7 @@ namespace cebag {
 enum KernelId : int {
     kKernForward = 0, kKernBagOf, kKernSort, kKernBwdPhase1, kKernBwdPhase2, kKernBwdCoo, kKernBwdWeights,
     kKernProbe, kKernBitmapRank, kKernSelect, kKernFreeSlots, kKernVictimRank, kKernPark, kKernFillRows, kKernWriteBack,
-    kKernFixup, kKernLfuCount, kKernFlush, kKernMoveRows, kKernFill, kKernCount
+    kKernFixup, kKernLfuCount, kKernFlush, kKernMoveRows, kKernFill, kKernIdHistogram, kKernCount
 };
 
 void count_launches(int n);

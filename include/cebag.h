@@ -163,6 +163,12 @@ CEBAG_API int cebag_ipc_close(void* ptr);
  * too large to initialise from one host thread. */
 CEBAG_API int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi, uint64_t seed, void* stream);
 
+/* id -> frequency histogram on the GPU: freq[id] += 1 for every id (int64[n], device); *bad_flag (device int32) is set
+ * when an id falls outside [0, num_rows).  Replaces the np.bincount counters of recsys/datasets/feature_counter.py:21-29
+ * whose output (ids_freq_mapping, int64[N]) feeds CachedParamMgr.reorder (A.1). */
+CEBAG_API int cebag_id_histogram(const int64_t* ids, int64_t n, int64_t* freq, int64_t num_rows, int32_t* bad_flag,
+                       void* stream);
+
 /* ---- cache manager (CachedParamMgr) ---------------------------------------------------------------------------- */
 CEBAG_API size_t cebag_prepare_workspace_bytes(const cebag_table* t, int64_t n_ids);
 

@@ -90,6 +90,35 @@ def test_struct_layouts_and_constants_match_header(tmp_path):
     assert int(got["CEBAG_FREQ_EMPTY"]) == _lib.FREQ_EMPTY
 
 
+def test_integration_stub_matches_binding():
+    """The ctypes stub printed in INTEGRATION.md declares the same struct layouts and argument lists as _lib.py (which
+    the layout test above ties to the header); the GPU suite executes the same block end to end."""
+    import ctypes
+    from cachedembedding_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"<!-- stub:begin -->\s*```python\n(.*?)```\s*<!-- stub:end -->", text, flags=re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    pairs = {"cebag_table": _lib.Table, "cebag_workspace": _lib.Workspace, "cebag_prepare_stats": _lib.PrepareStats,
+             "cebag_bag_args": _lib.BagArgs}
+    for name, cls in pairs.items():
+        stub = ns[name]
+        assert ctypes.sizeof(stub) == ctypes.sizeof(cls), name
+        assert [(f, getattr(stub, f).offset) for f, _ in stub._fields_] == \
+               [(f, getattr(cls, f).offset) for f, _ in cls._fields_], name
+    lib = _lib.load()
+    for fn in ("cebag_prepare_ids", "cebag_flush", "cebag_bag_forward", "cebag_bag_backward_fused",
+               "cebag_prepare_workspace_bytes", "cebag_backward_workspace_bytes"):
+        a, b = getattr(ns["lib"], fn).argtypes, getattr(lib, fn).argtypes
+        assert len(a) == len(b), fn
+        assert [ctypes.sizeof(x) for x in a] == [ctypes.sizeof(x) for x in b], fn
+
+
 def test_no_cpu_fallback():
     import cachedembedding_b200 as ce
     if torch.cuda.is_available():
@@ -208,6 +237,53 @@ def test_all_to_all_exchange_world2_gloo():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_exchange_worker, args=(world, port, results), nprocs=world, join=True)
+    assert all(results[r] for r in range(world)), dict(results)
+
+
+def _kjt_worker(rank, world, port, results):
+    """FusedKJTAllToAll against the semantics of the reference's KJTAllToAll (recsys/datasets/utils.py:21-54): every rank
+    gets, per key, rank 0's values then rank 1's ..., and lengths laid out [key][rank][sample]."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "shims"))
+    from torchrec.sparse.jagged_tensor import KeyedJaggedTensor
+    from cachedembedding_b200 import FusedKJTAllToAll
+    ok = True
+    for ragged in (True, False):
+        gen = torch.Generator().manual_seed(100 + rank + (7 if ragged else 0))
+        F, B = 3, 4
+        lengths = torch.randint(0, 4, (F * B,), generator=gen, dtype=torch.int32) if ragged \
+            else torch.ones(F * B, dtype=torch.int32)
+        values = torch.randint(0, 1000, (int(lengths.sum()),), generator=gen) + 10000 * rank
+        kjt = KeyedJaggedTensor(keys=[f"k{f}" for f in range(F)], values=values, lengths=lengths, stride=B)
+        coll = FusedKJTAllToAll(None, capacity=F * B * 3 if ragged else F * B, fixed_lengths=not ragged,
+                                kjt_factory=KeyedJaggedTensor.from_lengths_sync)
+        out = coll.all_to_all(kjt)
+        # expected, from everybody's inputs
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (values.tolist(), lengths.view(F, B).tolist()))
+        want_values, want_lengths = [], []
+        for f in range(F):
+            for vals, lens in everyone:
+                start = sum(sum(lens[k]) for k in range(f))
+                want_values += vals[start:start + sum(lens[f])]
+                want_lengths += lens[f]
+        ok = ok and out.values().tolist() == want_values and out.lengths().tolist() == want_lengths
+        ok = ok and out.stride() == B * world and out.keys() == kjt.keys()
+        ok = ok and out.values().dtype == values.dtype and out.lengths().dtype == lengths.dtype
+    results[rank] = ok
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_kjt_all_to_all_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_kjt_worker, args=(world, port, results), nprocs=world, join=True)
     assert all(results[r] for r in range(world)), dict(results)
 
 

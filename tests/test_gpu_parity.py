@@ -644,6 +644,43 @@ def test_reference_loop_with_async_copy_flag(strategy, stage_rows, adagrad):
         assert_maps_equal(mgr, omgr)
 
 
+def test_integration_stub_runs_verbatim():
+    """The binding stub of INTEGRATION.md, executed as printed: a cached table driven through the C ABI alone
+    (prepare_ids -> forward -> fused backward -> flush), against torch.nn.functional.embedding_bag + SGD."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"<!-- stub:begin -->\s*```python\n(.*?)```\s*<!-- stub:end -->", text, flags=re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)                      # the stub loads the library by its repo-relative path
+    try:
+        exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    gen = torch.Generator().manual_seed(17)
+    N, D, C, G = 3000, 128, 400, 300
+    host = (torch.randn(N, D, generator=gen) * 0.1).pin_memory()
+    ref = host.clone()
+    t, arrays = ns["make_table"](host, C)
+    pinned = torch.zeros(64, dtype=torch.int64).pin_memory()
+    offsets = torch.arange(G + 1)
+    evicted = 0
+    for _ in range(5):
+        ids = torch.randint(0, N, (G,), generator=gen)
+        grad = torch.randn(G, D, generator=gen)
+        out, stats = ns["train_step"](t, arrays, pinned, ids.cuda(), offsets.cuda(), grad.cuda(), 0.25)
+        want = torch.nn.functional.embedding_bag(ids, ref, offsets, mode="sum", include_last_offset=True)
+        close(out.cpu(), want)
+        ref.index_add_(0, ids, grad, alpha=-0.25)
+        assert stats.unique_hits + stats.unique_misses == int(torch.unique(ids).numel())
+        evicted += stats.evicted
+    assert evicted > 0
+    assert ns["flush"](t, pinned) == C
+    close(host, ref)
+
+
 # ---------------------------------------------------------------------------------------------------- BASELINE configs
 def test_baseline_config0_plumbing_matches_oracle():
     """BASELINE.json configs[0]: synthetic Kaggle-shape DLRM -- 26 tables x 1e5 rows, dim 16, batch 512 -- a few
