@@ -80,7 +80,7 @@ def _run_script(tmp_path, nproc, extra):
            "--dataset_dir", str(data), "--pin_memory", "--shuffle_batches", "--learning_rate", "1.",
            "--batch_size", "512", "--use_sparse_embed_grad", "--use_cache", "--use_freq", "--use_lfu",
            "--buffer_size", "0", "--use_overlap", "--cache_ratio", "0.01", "--prefetch_num", "8",
-           "--embedding_dim", "16", "--eval_acc", "--profile_dir", str(tmp_path / "tb")] + extra
+           "--embedding_dim", "16", "--dense_arch_layer_sizes", "64,32,16", "--eval_acc", "--profile_dir", str(tmp_path / "tb")] + extra
     out = subprocess.run(cmd, capture_output=True, text=True, env=_env(), cwd=str(tmp_path), timeout=900)
     log = out.stdout + out.stderr
     assert out.returncode == 0, log[-6000:]
