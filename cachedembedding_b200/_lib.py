@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
@@ -62,7 +62,12 @@ class Workspace(Structure):
     _fields_ = [("device", c_void_p), ("device_bytes", c_size_t), ("pinned", c_void_p),
                 ("copy_stream", c_void_p), ("copy_done_event", c_void_p), ("writeback_done_event", c_void_p),
                 ("victims_ready_event", c_void_p), ("stage", c_void_p), ("stage_state", c_void_p),
-                ("stage_rows", c_int64)]
+                ("stage_rows", c_int64),
+                ("dma_stream", c_void_p), ("dma_done_event", c_void_p), ("dma_wait_event", c_void_p),
+                ("dma_ring", c_void_p), ("dma_ring_state", c_void_p), ("dma_ring_rows", c_void_p),
+                ("dma_rows", c_int64), ("host_table_hostptr", c_void_p), ("host_state_hostptr", c_void_p),
+                ("prev_stage", c_void_p), ("prev_stage_state", c_void_p), ("retire_device", c_void_p),
+                ("retire_wait_event", c_void_p)]
 
 
 class PrepareStats(Structure):

@@ -18,6 +18,7 @@ single-row helpers), same attributes (``cuda_cached_weight``, ``weight``, ``idx_
 from __future__ import annotations
 
 import ctypes
+import os
 import sys
 import time
 from collections import deque
@@ -144,9 +145,17 @@ class CachedParamMgr(nn.Module):
         self._last_writeback = None   # event after the last write-back on a copy stream: flush waits for it
         self._defer_results = False   # look-ahead driver: results are read when the window is waited for
         self.stage_rows = 0           # 0: max(65536, C // 4) rows, capped at C
+        # DMA write-back (with a copy stream): parked victims leave through a copy engine into a pinned ring and host
+        # threads scatter them into the table (csrc/writeback_pool.cpp); CEBAG_DMA_WRITEBACK=0 keeps the zero-copy kernel
+        self.dma_writeback = os.environ.get("CEBAG_DMA_WRITEBACK", "1") != "0"
+        self._dma_stream = None
+        self._dma_ring = None         # pinned [rows, D] (+ row list, + state): one ring, the DMA stream is serial
+        self._last_evicted = 0        # E of the last call whose result has been read: the estimate for the next DMA
+        self._marked = deque()        # calls whose victims still carry markers: (call index, ws buffer, dma event, stage entry)
+        self._forwarding_from = None
         self._ws_ring = [None, None, None]       # [buffer, event after the call, write-back event]
         self._ws_next = 0
-        self._stage_ring = [None, None]          # [rows, state, write-back event]
+        self._stage_ring = [None, None, None]    # [rows, state, events to wait for before reuse]
         self._stage_next = 0
         self._results = torch.full((_RESULT_RING, 8), -1, dtype=torch.int64).pin_memory()
         self._result_next = 0
@@ -204,7 +213,7 @@ class CachedParamMgr(nn.Module):
             return self._own_copy_stream
         return None
 
-    def _workspace(self, t: _lib.Table, n_ids: int):
+    def _workspace(self, t: _lib.Table, n_ids: int, plumbing: bool = True):
         """Scratch + stream plumbing of one call.  Buffers come from small rings owned by the manager (nothing is
         allocated per call in steady state); a buffer is handed out again only after the calling stream has been made
         to wait for the kernels -- on either stream -- that still read it."""
@@ -221,10 +230,25 @@ class CachedParamMgr(nn.Module):
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         else:
             buf = entry[0]
-        ws = _lib.Workspace(buf.data_ptr(), buf.numel(), self._counters_pinned.data_ptr(), None, None, None, None,
-                            None, None, 0)
+        ws = _lib.Workspace()
+        ws.device, ws.device_bytes, ws.pinned = buf.data_ptr(), buf.numel(), self._counters_pinned.data_ptr()
         entry = [buf, None, None]
         self._ws_ring[i] = entry
+        if not plumbing:
+            return ws, entry, None
+        call = self._calls
+        # markers left by earlier calls (DMA write-back): everything older than the previous call is retired now -- its
+        # write-back is waited for on the device -- and the previous call's staging buffer is where re-admitted rows are
+        # filled from
+        while self._marked and self._marked[0][0] <= call - 2:
+            _, old_buf, dma_done, _ = self._marked.popleft()
+            ws.retire_device = old_buf.data_ptr()
+            ws.retire_wait_event = dma_done.cuda_event
+        prev_stage_entry = self._marked[-1][3] if self._marked else None
+        self._forwarding_from = prev_stage_entry
+        if prev_stage_entry is not None:
+            ws.prev_stage = prev_stage_entry[0].data_ptr()
+            ws.prev_stage_state = prev_stage_entry[1].data_ptr() if prev_stage_entry[1] is not None else None
         cstream = self._active_copy_stream()
         events = None
         if cstream is not None:
@@ -236,23 +260,49 @@ class CachedParamMgr(nn.Module):
             ws.writeback_done_event = wb_done.cuda_event
             entry[2] = wb_done
             events = (rows_done, wb_done)
-            # staging buffer for the victims (double-buffered: the write-back of the previous call may still read its own)
+            if prev_stage_entry is not None:
+                prev_stage_entry[2].append(rows_done)      # this call's fill may read that buffer
+            # staging buffer for the victims (a ring: the write-back of earlier calls may still read theirs)
             C, D = self.cuda_row_num, self.embedding_dim
             rows = self.stage_rows if self.stage_rows > 0 else max(65536, C // 4)
             rows = min(rows, C)
             j = self._stage_next
             self._stage_next = (j + 1) % len(self._stage_ring)
             st = self._stage_ring[j]
-            if st is not None and st[2] is not None:
-                cur.wait_event(st[2])
+            if st is not None:
+                for ev in st[2]:
+                    cur.wait_event(ev)
             if st is None or st[0].shape[0] != rows:
                 st = [torch.empty(rows, D, dtype=torch.float32, device=self.device),
-                      torch.empty(rows, dtype=torch.float32, device=self.device) if self.with_row_state else None, None]
-            st[2] = wb_done
+                      torch.empty(rows, dtype=torch.float32, device=self.device) if self.with_row_state else None, []]
+            st[2] = [wb_done]
             self._stage_ring[j] = st
             ws.stage = st[0].data_ptr()
             ws.stage_state = st[1].data_ptr() if st[1] is not None else None
             ws.stage_rows = rows
+            dma_rows = min(rows, int(self._last_evicted * 1.25) + 256) if self.dma_writeback and self._last_evicted > 0 else 0
+            if self.dma_writeback:
+                # markers are kept for every parked victim whenever the DMA path is configured (dma_rows may be 0)
+                if self._dma_stream is None:
+                    self._dma_stream = torch.cuda.Stream(device=self.device)
+                if self._dma_ring is None or self._dma_ring[0].shape[0] != rows:
+                    self._dma_ring = (torch.empty(rows, D, dtype=torch.float32).pin_memory(),
+                                      torch.empty(rows, dtype=torch.int32).pin_memory(),
+                                      torch.empty(rows, dtype=torch.float32).pin_memory() if self.with_row_state else None)
+                dma_done = torch.cuda.Event()
+                dma_done.record(self._dma_stream)
+                ws.dma_stream = self._dma_stream.cuda_stream
+                ws.dma_done_event = dma_done.cuda_event
+                if self._last_writeback is not None:
+                    ws.dma_wait_event = self._last_writeback.cuda_event
+                ws.dma_ring = self._dma_ring[0].data_ptr()
+                ws.dma_ring_rows = self._dma_ring[1].data_ptr()
+                ws.dma_ring_state = self._dma_ring[2].data_ptr() if self._dma_ring[2] is not None else None
+                ws.dma_rows = max(dma_rows, 1)
+                ws.host_table_hostptr = self.weight.data_ptr()
+                ws.host_state_hostptr = self.row_state.data_ptr() if self.row_state is not None else None
+                st[2].append(dma_done)
+                self._marked.append((call, buf, dma_done, st))
         if self._victims_ready is not None:
             ws.victims_ready_event = self._victims_ready.cuda_event
         return ws, entry, events
@@ -273,6 +323,7 @@ class CachedParamMgr(nn.Module):
             rc = self._lib.cebag_prepare_result_status(ctypes.byref(t), rec.data_ptr(), ctypes.byref(stats))
             _lib.check(rc)
             self._cuda_available_row_num = int(rec[7])
+            self._last_evicted = int(stats.evicted)
             self._cache_miss += stats.miss_lookups
             self._total_cache += n
             self._num_hits_history.append(int(stats.unique_hits))
@@ -379,7 +430,10 @@ class CachedParamMgr(nn.Module):
         self.wait_rows()
         self._wait_writeback()
         t = self._table()
-        ws, entry, _ = self._workspace(t, 1)
+        if self._dma_stream is not None:
+            self._dma_stream.synchronize()      # every DMA write-back is in the table; flush clears the markers
+        self._marked.clear()
+        ws, entry, _ = self._workspace(t, 1, plumbing=False)
         written = ctypes.c_int64(0)
         _lib.check(self._lib.cebag_flush(ctypes.byref(t), ctypes.byref(ws), ctypes.byref(written), _stream_ptr()))
         if self._own_copy_stream is not None:
@@ -417,6 +471,9 @@ class CachedParamMgr(nn.Module):
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream())
         entry[1] = done
+        if copy_events is None and self._forwarding_from is not None:
+            self._forwarding_from[2].append(done)      # this call's fill (on this stream) may have read that buffer
+        self._forwarding_from = None
         self._pending.append((idx, done, n))
         if copy_events is not None:
             self._rows_ready, self._last_writeback = copy_events

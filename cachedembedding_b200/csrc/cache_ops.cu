@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "profile.cuh"
+#include "writeback_pool.h"
 
 namespace cebag {
 
@@ -365,7 +366,7 @@ emit_free_slots_kernel(const int32_t* __restrict__ counters, const int32_t* __re
 __global__ void __launch_bounds__(kThreads)
 commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ counters,
                         const int32_t* __restrict__ miss_rows, const int32_t* __restrict__ free_slots,
-                        int32_t* __restrict__ victim_rows) {
+                        int32_t* __restrict__ victim_rows, int32_t* __restrict__ fill_src) {
     const int64_t m = counters[kCtrAdmit];
     const int32_t epoch = counters[kCtrEpoch];
     for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kThreads) {
@@ -374,6 +375,10 @@ commit_admission_kernel(const cebag_table t, const int32_t* __restrict__ counter
         const int32_t old_row = t.slot2row[slot];
         victim_rows[j] = old_row;
         if (old_row >= 0) t.row2slot[old_row] = -2 - slot;
+        // a marker left by an earlier call: the row's write-back may still be in flight, its last value is entry
+        // -2 - marker of that call's staging buffer
+        const int32_t before = t.row2slot[row];
+        fill_src[j] = before <= -2 ? -2 - before : -1;
         t.slot2row[slot] = row;
         t.row2slot[row] = slot;
         t.slot_epoch[slot] = epoch;
@@ -414,14 +419,34 @@ mark_victims_kernel(const cebag_table t, const int32_t* __restrict__ counters, c
 // of the bitmap.
 __global__ void __launch_bounds__(kThreads)
 resolve_victims_kernel(const cebag_table t, const int32_t* __restrict__ counters,
-                       const int32_t* __restrict__ victims_sorted, int32_t* __restrict__ victim_slots) {
+                       const int32_t* __restrict__ victims_sorted, int32_t* __restrict__ victim_slots,
+                       int64_t marked_rows) {
     const int64_t e = counters[kCtrEvict];
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < e; i += (int64_t)gridDim.x * kThreads) {
         const int32_t row = victims_sorted[i];
         victim_slots[i] = -2 - t.row2slot[row];
-        t.row2slot[row] = -1;
+        // parked victims whose write-back is asynchronous keep a marker (their index in the staging buffer)
+        t.row2slot[row] = i < marked_rows ? (int32_t)(-2 - i) : -1;
         t.miss_bitmap[row >> 5] = 0u;   // every bit of this word is a victim of this call
     }
+}
+
+// markers of an earlier call whose write-back has completed: the host table is current again
+__global__ void __launch_bounds__(kThreads)
+retire_markers_kernel(const cebag_table t, const int32_t* __restrict__ old_counters,
+                      const int32_t* __restrict__ old_victims_sorted, int64_t bound) {
+    int64_t e = old_counters[kCtrEvict];
+    if (e > bound) e = bound;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < e; i += (int64_t)gridDim.x * kThreads) {
+        const int32_t row = old_victims_sorted[i];
+        if (t.row2slot[row] == (int32_t)(-2 - i)) t.row2slot[row] = -1;      // not re-admitted since
+    }
+}
+
+// flush: no marker survives (every write-back has completed by then)
+__global__ void __launch_bounds__(kThreads) normalize_markers_kernel(const cebag_table t) {
+    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < t.num_rows; r += (int64_t)gridDim.x * kThreads)
+        if (t.row2slot[r] < -1) t.row2slot[r] = -1;
 }
 
 // ---- row movement -----------------------------------------------------------------------------------------------------------
@@ -440,8 +465,10 @@ __device__ __forceinline__ void warp_copy_row(float* __restrict__ dst, const flo
 // Row traffic of one call, one warp per row.  All lists are in ascending HOST ROW order.
 //   kParkVictims : cache[victim_slots[i]] -> stage[i]                       i in [0, min(E, stage_rows))    HBM -> HBM
 //   kWriteDirect : cache[victim_slots[i]] -> host_table[victims_sorted[i]]  i in [first, E)                 D2H
-//   kWriteParked : stage[i]               -> host_table[victims_sorted[i]]  i in [0, min(E, stage_rows))    D2H
+//   kWriteParked : stage[i]               -> host_table[victims_sorted[i]]  i in [dma_rows, min(E, stage_rows))  D2H
+//                  (entries below dma_rows leave through the copy engine + host threads instead)
 //   kFill        : host_table[miss_rows[j]] -> cache[free_slots[j]]         j in [0, M)                     H2D
+//                  or prev_stage[fill_src[j]] -> cache[free_slots[j]] for rows whose write-back may be in flight
 // The row-wise Adagrad state travels with the row.
 enum : int { kParkVictims = 0, kWriteDirect = 1, kWriteParked = 2, kFill = 3 };
 
@@ -453,6 +480,10 @@ struct RowLists {
     float* stage;
     float* stage_state;
     int64_t stage_rows;
+    int64_t dma_rows;
+    const int32_t* fill_src;
+    const float* prev_stage;
+    const float* prev_stage_state;
 };
 
 template <bool VEC, int WHAT>
@@ -466,14 +497,18 @@ move_window_rows_kernel(const cebag_table t, const int32_t* __restrict__ counter
     const int64_t e = counters[kCtrEvict];
     const int64_t parked = L.stage ? (e < L.stage_rows ? e : L.stage_rows) : 0;
     int64_t lo = 0, hi = 0;
-    if (WHAT == kParkVictims || WHAT == kWriteParked) hi = parked;
+    if (WHAT == kParkVictims) hi = parked;
+    else if (WHAT == kWriteParked) { lo = L.dma_rows < parked ? L.dma_rows : parked; hi = parked; }
     else if (WHAT == kWriteDirect) { lo = parked; hi = e; }
     else hi = counters[kCtrAdmit];
     for (int64_t j = lo + warp; j < hi; j += num_warps) {
         if (WHAT == kFill) {
             const int32_t slot = L.free_slots[j], row = L.miss_rows[j];
-            warp_copy_row<VEC>(t.cache + (int64_t)slot * dim, t.host_table + (int64_t)row * dim, dim, lane);
-            if (lane == 0 && with_state) t.cache_state[slot] = t.host_state[row];
+            const int32_t fwd = L.prev_stage ? L.fill_src[j] : -1;
+            const float* src = fwd >= 0 ? L.prev_stage + (int64_t)fwd * dim : t.host_table + (int64_t)row * dim;
+            warp_copy_row<VEC>(t.cache + (int64_t)slot * dim, src, dim, lane);
+            if (lane == 0 && with_state)
+                t.cache_state[slot] = (fwd >= 0 && L.prev_stage_state) ? L.prev_stage_state[fwd] : t.host_state[row];
         } else if (WHAT == kParkVictims) {
             const int32_t slot = L.victim_slots[j];
             warp_copy_row<VEC>(L.stage + j * dim, t.cache + (int64_t)slot * dim, dim, lane);
@@ -611,7 +646,7 @@ lfu_count_kernel(const cebag_table t, const int32_t* __restrict__ counters, cons
 }
 
 struct PrepLayout {
-    size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, total;
+    size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, fill_src, total;
     int64_t bitmap_blocks, words, hit_words;
 };
 
@@ -624,9 +659,10 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     L.hit_words = ceil_div(C, 16) * 4;              // the hit flags as 32-bit words (4 slots each)
     L.bitmap_blocks = ceil_div(L.words, kWordsPerBlock);
     size_t off = 0;
+    // everything but miss_pos sits at an offset that does not depend on n: a later call finds the counters and the
+    // victim list of this one (retire_device) without knowing its n
     L.counters = off; off += align(kNumCounters * 4);
     L.select = off; off += align(sizeof(SelectState));
-    L.miss_pos = off; off += align((size_t)nn * 4);
     L.miss_rows = off; off += align((size_t)C * 4);
     L.free_slots = off; off += align((size_t)C * 4);
     L.victim_rows = off; off += align((size_t)C * 4);
@@ -635,9 +671,13 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     L.bitmap_sums = off; off += align((size_t)(L.bitmap_blocks + 1) * 4);
     int64_t longest = C > L.bitmap_blocks ? C : L.bitmap_blocks;
     L.scan_ws = off; off += align(scan_workspace_bytes(longest));
+    L.fill_src = off; off += align((size_t)C * 4);
+    L.miss_pos = off; off += align((size_t)nn * 4);
     L.total = off;
     return L;
 }
+
+int sgrid_for_retire(int64_t cache_rows) { return grid_for(cache_rows < 262144 ? cache_rows : 262144, kThreads, 8); }
 
 bool table_vec_ok(const cebag_table* t) {
     return t->dim % 4 == 0 && aligned16(t->cache) && aligned16(t->host_table);
@@ -690,7 +730,8 @@ __global__ void move_one_kernel(const cebag_table t, int32_t row, int32_t slot, 
 template <int WHAT>
 int launch_rows(const cebag_table* t, const int32_t* counters, const RowLists& lists, int grid, int threads,
                 cudaStream_t stream) {
-    if (table_vec_ok(t) && (WHAT == kFill || WHAT == kWriteDirect || aligned16(lists.stage)))
+    if (table_vec_ok(t) && (WHAT == kWriteDirect || (WHAT == kFill && aligned16(lists.prev_stage)) ||
+                            (WHAT != kFill && aligned16(lists.stage))))
         move_window_rows_kernel<true, WHAT><<<grid, threads, 0, stream>>>(*t, counters, lists);
     else
         move_window_rows_kernel<false, WHAT><<<grid, threads, 0, stream>>>(*t, counters, lists);
@@ -743,8 +784,29 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
     int32_t* flags_b = reinterpret_cast<int32_t*>(base + L.flags_b);
     int32_t* bitmap_sums = reinterpret_cast<int32_t*>(base + L.bitmap_sums);
     int32_t* scan_ws = reinterpret_cast<int32_t*>(base + L.scan_ws);
+    int32_t* fill_src = reinterpret_cast<int32_t*>(base + L.fill_src);
     const int64_t C = t->cache_rows;
     const int64_t admit_bound = n < C ? n : C;          // M <= min(n, C) whenever the call is accepted
+    cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
+    const bool park = cstream != stream && ws->stage != nullptr && ws->stage_rows > 0;
+    // DMA write-back: the first dma_rows parked victims leave through a copy engine and the host threads
+    const bool dma = park && ws->dma_stream != nullptr && ws->dma_rows > 0 && ws->dma_ring && ws->dma_ring_rows &&
+                     ws->host_table_hostptr;
+    const int64_t dma_rows = dma ? (ws->dma_rows < ws->stage_rows ? ws->dma_rows : ws->stage_rows) : 0;
+    CEBAG_REQUIRE(!(ws->dma_stream && ws->dma_rows > 0) || dma, "DMA write-back needs copy_stream, stage, dma_ring, "
+                  "dma_ring_rows and host_table_hostptr");
+    CEBAG_REQUIRE(!dma || !(t->host_state && t->cache_state) || (ws->dma_ring_state && ws->stage_state && ws->host_state_hostptr),
+                  "DMA write-back of a table with row state needs stage_state, dma_ring_state and host_state_hostptr");
+
+    if (ws->retire_device) {   // markers of an earlier call: its write-back has completed, the host table is current
+        const char* old = reinterpret_cast<const char*>(ws->retire_device);
+        if (ws->retire_wait_event)
+            CEBAG_CUDA_CHECK(cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(ws->retire_wait_event), 0));
+        retire_markers_kernel<<<sgrid_for_retire(C), kThreads, 0, stream>>>(
+            *t, reinterpret_cast<const int32_t*>(old + L.counters), reinterpret_cast<const int32_t*>(old + L.flags_a), C);
+        count_launches(1);
+        CEBAG_LAUNCH_CHECK();
+    }
     const int sgrid = grid_for(C, kThreads, 8);
     const bool lfu = t->strategy == CEBAG_EVICT_LFU;
 
@@ -801,7 +863,7 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         if (rc) return rc;
         emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(counters, flags_a, flags_b, C, free_slots);
         commit_admission_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, miss_rows,
-                                                                                            free_slots, victim_rows);
+                                                                                            free_slots, victim_rows, fill_src);
         stamp_hits_kernel<<<grid_for(L.hit_words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.hit_words);
         CEBAG_LAUNCH_CHECK();
     }
@@ -826,7 +888,8 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         if (rc) return rc;
         bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
                                                                               flags_a, C, counters + kCtrEvict);
-        resolve_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, flags_a, flags_b);
+        resolve_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, flags_a, flags_b,
+                                                                                            dma ? ws->stage_rows : 0);
         clear_bitmap_if_rejected_kernel<<<grid_for(L.words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.words);
         end_call_kernel<<<1, 32, 0, stream>>>(*t, counters, n, result_dev);
         CEBAG_LAUNCH_CHECK();
@@ -838,8 +901,6 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
     // 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 46 of 51 GB/s).
     static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
     static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
-    cudaStream_t cstream = ws->copy_stream ? reinterpret_cast<cudaStream_t>(ws->copy_stream) : stream;
-    const bool park = cstream != stream && ws->stage != nullptr && ws->stage_rows > 0;
     RowLists lists;
     lists.miss_rows = miss_rows;
     lists.free_slots = free_slots;
@@ -848,6 +909,10 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
     lists.stage = park ? ws->stage : nullptr;
     lists.stage_state = park ? ws->stage_state : nullptr;
     lists.stage_rows = park ? ws->stage_rows : 0;
+    lists.dma_rows = dma_rows;
+    lists.fill_src = fill_src;
+    lists.prev_stage = ws->prev_stage;
+    lists.prev_stage_state = ws->prev_stage_state;
     // the victims' rows (and the slots the fill overwrites) may still be in use by an earlier window
     if (ws->victims_ready_event)
         CEBAG_CUDA_CHECK(cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(ws->victims_ready_event), 0));
@@ -862,6 +927,41 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         if (!committed) CEBAG_CUDA_CHECK(cudaEventCreateWithFlags(&committed, cudaEventDisableTiming));
         CEBAG_CUDA_CHECK(cudaEventRecord(committed, stream));
         CEBAG_CUDA_CHECK(cudaStreamWaitEvent(cstream, committed, 0));
+        if (dma) {
+            cudaStream_t dstream = reinterpret_cast<cudaStream_t>(ws->dma_stream);
+            CEBAG_CUDA_CHECK(cudaStreamWaitEvent(dstream, committed, 0));
+            if (ws->dma_wait_event)
+                CEBAG_CUDA_CHECK(cudaStreamWaitEvent(dstream, reinterpret_cast<cudaEvent_t>(ws->dma_wait_event), 0));
+            const size_t row_bytes = (size_t)t->dim * sizeof(float);
+            CEBAG_CUDA_CHECK(cudaMemcpyAsync(ws->dma_ring, ws->stage, (size_t)dma_rows * row_bytes, cudaMemcpyDeviceToHost, dstream));
+            CEBAG_CUDA_CHECK(cudaMemcpyAsync(ws->dma_ring_rows, flags_a, (size_t)dma_rows * sizeof(int32_t),
+                                             cudaMemcpyDeviceToHost, dstream));
+            const bool with_state = t->host_state && t->cache_state;
+            if (with_state)
+                CEBAG_CUDA_CHECK(cudaMemcpyAsync(ws->dma_ring_state, ws->stage_state, (size_t)dma_rows * sizeof(float),
+                                                 cudaMemcpyDeviceToHost, dstream));
+            WritebackJob* job = new WritebackJob();
+            job->host_table = ws->host_table_hostptr;
+            job->host_state = with_state ? ws->host_state_hostptr : nullptr;
+            job->ring = ws->dma_ring;
+            job->ring_state = with_state ? ws->dma_ring_state : nullptr;
+            job->rows = ws->dma_ring_rows;
+            job->ring_rows = dma_rows;
+            job->dim = t->dim;
+            job->evicted = &result->evicted;
+            job->status = &result->status;
+            cudaError_t e = cudaLaunchHostFunc(dstream, [](void* p) {
+                WritebackJob* j = reinterpret_cast<WritebackJob*>(p);
+                run_writeback_job(*j);
+                delete j;
+            }, job);
+            if (e != cudaSuccess) {
+                delete job;
+                CEBAG_CUDA_CHECK(e);
+            }
+            if (ws->dma_done_event)
+                CEBAG_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ws->dma_done_event), dstream));
+        }
     }
     {   // victims that are not parked must leave their slots before the fill overwrites them
         KernelScope scope(kKernWriteBack, cstream);
@@ -949,6 +1049,8 @@ extern "C" int cebag_flush(const cebag_table* t, const cebag_workspace* ws, int6
         KernelScope scope(kKernFlush, stream);
         if (table_vec_ok(t)) flush_kernel<true><<<grid, kThreads, 0, stream>>>(*t, counters);
         else flush_kernel<false><<<grid, kThreads, 0, stream>>>(*t, counters);
+        normalize_markers_kernel<<<grid_for(t->num_rows, kThreads, 8), kThreads, 0, stream>>>(*t);
+        count_launches(1);
     }
     CEBAG_LAUNCH_CHECK();
     CEBAG_CUDA_CHECK(cudaMemcpyAsync(ws->pinned, counters, kNumCounters * 4, cudaMemcpyDeviceToHost, stream));

@@ -8,8 +8,12 @@ timers end in torch.cuda.synchronize()).  Here three stre
   side stream    : prepare_ids of window k+1 -- id->slot probe, victim selection, map commit, LFU update, parking of
                    the victims in an HBM staging buffer -- and, if asked, the gradient-independent half of each
                    batch's fused backward (radix sort by slot)
-  copy stream    : the PCIe row traffic of that prepare_ids (fill of the missed rows, then write-back of the parked
-                   victims); only the fill is waited for by the forward of window k+1
+  copy stream    : the PCIe row traffic of that prepare_ids (fill of the missed rows -- a zero-copy gather kernel --
+                   then the zero-copy write-back of whatever the DMA path does not take); only the fill is waited for
+                   by the forward of window k+1
+  DMA stream     : the parked victims go D2H as ONE contiguous copy-engine transfer into a pinned ring, in parallel
+                   with the fill, and host threads scatter them into the table (cache_mgr.dma_writeback); a row that
+                   is missed again while its write-back is in flight is filled from the staging buffer
 
 prepare_ids never waits for the GPU (cebag_prepare_ids_async), so `submit` costs the host a few dozen kernel launches
 and may be called anywhere inside window k -- the earlier the better: right after the window's first step has been
@@ -167,6 +171,8 @@ class LookaheadPrefetcher:
         self.stream.synchronize()
         if self.copy_stream is not None:
             self.copy_stream.synchronize()
+        if self.mgr._dma_stream is not None:
+            self.mgr._dma_stream.synchronize()
         for ev in self._fences.values():
             ev.synchronize()
         self.mgr._harvest()

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CEBAG_ABI_VERSION 6
+#define CEBAG_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define CEBAG_API __attribute__((visibility("default")))
@@ -108,6 +108,27 @@ typedef struct cebag_workspace {
                                  the fill does not wait for their write-back over PCIe                        */
     float* stage_state;       /* fp32[stage_rows] or NULL (row-wise Adagrad state of the parked victims)   */
     int64_t stage_rows;
+    /* DMA write-back (needs copy_stream + stage): the first dma_rows parked victims leave through a copy engine -- one
+     * contiguous cudaMemcpyAsync into a pinned ring -- and host threads scatter them into the table; the rest of the
+     * parked victims is written by the zero-copy kernel as before.  dma_rows is the caller's ESTIMATE of E (E itself
+     * only exists on the device): the host side scatters min(E, dma_rows) rows.  While a write-back is in flight the
+     * victim's row2slot entry is the marker -2 - (its index in `stage`): a later call that re-admits the row fills it
+     * from that staging buffer (prev_stage) instead of the host table; `retire_device` names the workspace of an
+     * earlier call whose markers are cleared once its write-back has completed (retire_wait_event). */
+    void*  dma_stream;        /* cudaStream_t of the D2H copies and of the host scatter                    */
+    void*  dma_done_event;    /* cudaEvent_t recorded on dma_stream once those rows are in the host table   */
+    void*  dma_wait_event;    /* optional cudaEvent_t dma_stream waits for first (zero-copy write-backs of the
+                                 previous call, which may target the same host rows)                        */
+    float* dma_ring;          /* pinned host fp32[dma_rows, D]                                             */
+    float* dma_ring_state;    /* pinned host fp32[dma_rows] or NULL                                        */
+    int32_t* dma_ring_rows;   /* pinned host int32[dma_rows]: host row of every ring entry                 */
+    int64_t dma_rows;
+    float* host_table_hostptr;/* HOST addresses of cebag_table.host_table / host_state (for the host threads) */
+    float* host_state_hostptr;
+    const float* prev_stage;  /* staging buffer the markers currently in row2slot point into, or NULL      */
+    const float* prev_stage_state;
+    const void* retire_device;/* `device` of the earlier call whose markers are to be cleared, or NULL     */
+    void*  retire_wait_event; /* cudaEvent_t `stream` waits for before clearing them                       */
 } cebag_workspace;
 
 /* What one prepare_ids call did (upstream: num_hits_history / num_miss_history / num_write_back_history,

@@ -441,14 +441,18 @@ def test_module_surface():
 
 # ---------------------------------------------------------------------------------------------------- look-ahead overlap
 @pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
-@pytest.mark.parametrize("early,stage_rows", [(True, 0), (False, 0), (True, 7)])
-def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy, early, stage_rows):
+@pytest.mark.parametrize("early,stage_rows,dma", [(True, 0, True), (False, 0, True), (True, 7, True), (True, 0, False),
+                                                   (True, 0, "slow")])
+def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy, early, stage_rows, dma, monkeypatch):
     """prepare_ids of window k+1 on a side stream while window k trains: slot ids and maps bit-exact against the
     oracle run with the same two-window protection; pooled sums / final table within 1e-5 of it.
     early: window k+1 is submitted right after the FIRST step of window k (the order bench.py uses), otherwise after its
     last step.  stage_rows = 7: most victims do not fit the staging buffer and are written back straight from their
-    slots before the fill."""
+    slots before the fill.  dma: parked victims leave through the copy engine + host threads ("slow": every host
+    scatter is delayed by 20 ms, so rows that are missed again are served from the staging buffer or not at all)."""
     ce = _mods()
+    if dma == "slow":
+        monkeypatch.setenv("CEBAG_WB_DELAY_US", "20000")
     gen = torch.Generator().manual_seed(33)
     N, D, F, B, P = 6000, 128, 4, 64, 2
     weight = torch.randn(N, D, generator=gen) * 0.01
@@ -465,6 +469,7 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     windows = [[(torch.rand(F * B, generator=gen) ** 2 * N).long().clamp_(0, N - 1) for _ in range(P)] for _ in range(8)]
     grads = [[torch.randn(F * B, D, generator=gen) for _ in range(P)] for _ in range(8)]
     model.cache_weight_mgr.stage_rows = stage_rows
+    model.cache_weight_mgr.dma_writeback = bool(dma)
     pf = ce.LookaheadPrefetcher(model)
     assert model.cache_weight_mgr.protect_windows == 2
     h = pf.submit([w.pin_memory() for w in windows[0]], offsets=offsets.cuda())   # host ids: H2D rides the side stream
@@ -590,8 +595,9 @@ def _lib_state_mask(tensor):
 
 
 @pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
-@pytest.mark.parametrize("stage_rows,adagrad", [(0, False), (5, False), (0, True)])
-def test_reference_loop_with_async_copy_flag(strategy, stage_rows, adagrad):
+@pytest.mark.parametrize("stage_rows,adagrad,dma", [(0, False, True), (5, False, True), (0, True, True), (0, False, False),
+                                                    (0, True, "slow")])
+def test_reference_loop_with_async_copy_flag(strategy, stage_rows, adagrad, dma, monkeypatch):
     """The reference's loop, unchanged (/root/reference/recsys/dlrm_main.py:245-279 with the flag of :121,354):
     set_cache_mgr_async_copy(True); one prepare_ids over the concatenated window on the CURRENT stream; then P forward /
     backward steps with cache_op off.  The row traffic runs on the manager's copy stream (victims parked in HBM, fill,
@@ -609,6 +615,9 @@ def test_reference_loop_with_async_copy_flag(strategy, stage_rows, adagrad):
     model.set_cache_mgr_async_copy(True)
     mgr, omgr = model.cache_weight_mgr, omodel.cache_weight_mgr
     mgr.stage_rows = stage_rows
+    mgr.dma_writeback = bool(dma)
+    if dma == "slow":
+        monkeypatch.setenv("CEBAG_WB_DELAY_US", "20000")
     oopt = torch.optim.SGD(omodel.parameters(), lr=0.5)
     offsets = torch.arange(F * B + 1)
     state = np.zeros(N)
