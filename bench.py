@@ -274,6 +274,7 @@ def run_b200(args):
         def __init__(self, batches, host_inputs, overlap=overlap):
             self.batches, self.host, self.overlap = batches, host_inputs, overlap
             self.w, self.slots, self.handles, self.h2d = -1, None, {}, 0
+            self.trace = []
             self.plan = dict(offsets=offsets) if not args.no_plan_side else {}
 
         def ids(self, w):
@@ -305,6 +306,10 @@ def run_b200(args):
                         self.slots = torch.chunk(mgr.prepare_ids(win), P)
                     self.w = w
                 out = embed_step(self.slots[j])
+                if args.trace_steps:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    self.trace.append((s, ev, time.perf_counter()))
                 if self.host:
                     result_host.copy_(out.view(-1)[:D], non_blocking=True)
                     d2h += D * 4
@@ -326,8 +331,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         h2d, d2h = runner.run(first, count)
         e1.record()
+        if args.trace_steps and rank == 0 and runner.trace:
+            torch.cuda.synchronize()
+            s0, ev0, h0 = [t for t in runner.trace if t[0] >= first][0]
+            print(f"first timed step {s0}: gpu +{e0.elapsed_time(ev0):.3f} ms after the start event, host "
+                  f"+{(h0 - t_host) * 1e3:.3f} ms; whole region {e0.elapsed_time(e1):.3f} ms", file=sys.stderr)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -358,6 +369,10 @@ def run_b200(args):
     hist0 = len(mgr.num_miss_history)
     ms_total, _, _ = timed(value_runner, W, K)
     value_runner.finish()
+    if args.trace_steps and rank == 0:
+        tr = [t for t in value_runner.trace if t[0] >= W]
+        for (s0, e0, h0), (s1, e1, h1) in zip(tr[:-1], tr[1:]):
+            print(f"step {s1}: gpu +{e0.elapsed_time(e1):.3f} ms, host +{(h1 - h0) * 1e3:.3f} ms", file=sys.stderr)
     gpu_launches = _lib.launch_count() - launches0
     miss_u = sum(mgr.num_miss_history[hist0:])
     hit_u = sum(mgr.num_hits_history[hist0:])
@@ -590,6 +605,7 @@ def main():
     ap.add_argument("--parallelism", default="table", choices=["table", "column"],
                     help="N > 1: table-wise sharding (BASELINE.json configs[3]) or the reference's default column-wise bag")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the untimed parity leg")
+    ap.add_argument("--trace-steps", action="store_true", help="print GPU / host time between consecutive timed steps")
     ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     args = ap.parse_args()

@@ -17,7 +17,7 @@ ABI_VERSION = 7
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
 PREPARE_PENDING = -1
-STATE_AVAIL, STATE_EPOCH, STATE_CALLS, STATE_WORDS = 0, 1, 2, 8
+STATE_AVAIL, STATE_EPOCH, STATE_CALLS, STATE_MAXFREQ, STATE_WORDS = 0, 1, 2, 3, 8
 EVICT_LFU, EVICT_DATASET = 1, 2
 MODE_SUM, MODE_MEAN = 0, 1
 OPT_SGD, OPT_ROWWISE_ADAGRAD = 0, 1
@@ -33,6 +33,7 @@ EXPORTS = (
     "cebag_host_alloc", "cebag_host_free", "cebag_host_register", "cebag_host_unregister",
     "cebag_host_device_pointer", "cebag_fill_uniform", "cebag_id_histogram",
     "cebag_device_alloc", "cebag_device_free", "cebag_ipc_export", "cebag_ipc_import", "cebag_ipc_close",
+    "cebag_peer_barrier",
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_prepare_ids_async", "cebag_prepare_result_status",
     "cebag_flush", "cebag_preload", "cebag_admit_row", "cebag_evict_slot", "cebag_available_rows",
     "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused", "cebag_bag_backward_plan",
@@ -126,6 +127,7 @@ def _declare(lib):
     lib.cebag_ipc_export.argtypes = [c_void_p, ctypes.c_char_p]
     lib.cebag_ipc_import.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
     lib.cebag_ipc_close.argtypes = [c_void_p]
+    lib.cebag_peer_barrier.argtypes = [POINTER(Exchange), c_int32, ctypes.c_uint32, c_void_p, c_void_p]
     lib.cebag_prepare_workspace_bytes.argtypes = [POINTER(Table), c_int64]
     lib.cebag_prepare_workspace_bytes.restype = c_size_t
     lib.cebag_prepare_ids.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),

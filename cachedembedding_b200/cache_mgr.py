@@ -146,8 +146,10 @@ class CachedParamMgr(nn.Module):
         self._defer_results = False   # look-ahead driver: results are read when the window is waited for
         self.stage_rows = 0           # 0: max(65536, C // 4) rows, capped at C
         # DMA write-back (with a copy stream): parked victims leave through a copy engine into a pinned ring and host
-        # threads scatter them into the table (csrc/writeback_pool.cpp); CEBAG_DMA_WRITEBACK=0 keeps the zero-copy kernel
-        self.dma_writeback = os.environ.get("CEBAG_DMA_WRITEBACK", "1") != "0"
+        # threads scatter them into the table (csrc/writeback_pool.cpp).  Off by default (CEBAG_DMA_WRITEBACK=1 or this
+        # attribute turn it on): at Criteo-1TB the row traffic is no longer the critical path, and the zero-copy kernel
+        # keeps the host threads out of the loop
+        self.dma_writeback = os.environ.get("CEBAG_DMA_WRITEBACK", "0") == "1"
         self._dma_stream = None
         self._dma_ring = None         # pinned [rows, D] (+ row list, + state): one ring, the DMA stream is serial
         self._last_evicted = 0        # E of the last call whose result has been read: the estimate for the next DMA

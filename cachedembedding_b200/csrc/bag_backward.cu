@@ -451,9 +451,11 @@ BwdLayout bwd_layout(int64_t n, int dim) {
     return L;
 }
 
+// bits that tell all slot ids [0, C) apart AND from the all-ones pattern of an invalid slot (-1), which the masked
+// digits of the sort would otherwise alias with slot 2^bits - 1
 int key_bits_for(int32_t cache_rows) {
     int bits = 1;
-    while (((int64_t)1 << bits) < (int64_t)cache_rows) ++bits;
+    while (((int64_t)1 << bits) < (int64_t)cache_rows + 1) ++bits;
     return bits;
 }
 

@@ -20,6 +20,7 @@ struct BagParams {
     int64_t layout_batch;     // B (sample-major layout)
     int64_t layout_features;  // F = num_bags / B
     int32_t dim;              // D floats
+    int32_t cache_rows;       // C
     int32_t chunks;           // row width in VT chunks (D/4 or D)
     int32_t offsets_are_64;
     int32_t include_last;
@@ -162,5 +163,8 @@ static inline RowShape row_shape(int dim, bool all_aligned16) {
     } while (0)
 
 int fill_bag_params(const cebag_bag_args* a, BagParams* p, const RowShape& rs);
+
+// TMA-driven forward (bag_forward_tma.cu): returns true when it took the call (*rc = its status)
+bool bag_forward_tma_launch(const cebag_bag_args* a, const BagParams& p, float* out, cudaStream_t stream, int* rc);
 
 }  // namespace cebag

@@ -135,6 +135,7 @@ int fill_bag_params(const cebag_bag_args* a, BagParams* p, const RowShape& rs) {
     p->num_bags = a->num_bags;
     p->padding_idx = a->padding_idx >= 0 ? a->padding_idx : -1;
     p->dim = a->dim;
+    p->cache_rows = a->cache_rows;
     p->chunks = rs.chunks;
     p->offsets_are_64 = a->offsets_are_64;
     p->include_last = a->include_last_offset;
@@ -184,6 +185,10 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     BagParams p;
     int rc = fill_bag_params(a, &p, rs);
     if (rc) return rc;
+    {   // pooling-factor-1 style calls: TMA row gather (bulk async copies through shared memory)
+        int tma_rc = CEBAG_OK;
+        if (bag_forward_tma_launch(a, p, out, stream, &tma_rc)) return tma_rc;
+    }
     // rows in flight per group (tunable: CEBAG_FWD_UNROLL = 4 | 8)
     static const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
     static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 16);

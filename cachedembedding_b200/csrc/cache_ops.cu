@@ -262,6 +262,13 @@ __device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, int32_
     return true;
 }
 
+// LFU: every counter of an occupied slot is <= dev_state[MAXFREQ], so a radix pass above that value's highest byte
+// sees digit 0 everywhere and changes nothing (the counters are int64, the counts rarely need more than 3-4 bytes)
+__device__ __forceinline__ bool select_pass_is_void(const cebag_table& t, int shift) {
+    return t.strategy == CEBAG_EVICT_LFU && shift > 0 &&
+           ((unsigned long long)t.dev_state[CEBAG_STATE_MAXFREQ] >> shift) == 0ull;
+}
+
 // how many occupied slots may be evicted (only needed when more than the current window is protected)
 __global__ void __launch_bounds__(kThreads)
 count_evictable_kernel(const cebag_table t, int32_t* __restrict__ counters) {
@@ -282,6 +289,7 @@ select_hist_kernel(const cebag_table t, const int32_t* __restrict__ counters, Se
                    int first_pass) {
     __shared__ int h[256];
     if (counters[kCtrEvict] == 0) return;
+    if (select_pass_is_void(t, shift)) return;
     const int32_t epoch = counters[kCtrEpoch];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -297,10 +305,11 @@ select_hist_kernel(const cebag_table t, const int32_t* __restrict__ counters, Se
 }
 
 __global__ void __launch_bounds__(256)
-select_choose_kernel(const int32_t* __restrict__ counters, SelectState* __restrict__ st, int shift) {
+select_choose_kernel(const cebag_table t, const int32_t* __restrict__ counters, SelectState* __restrict__ st, int shift) {
     // 256 threads, one per bin: the digit whose cumulative count first reaches k
     __shared__ int32_t warp_sums[32];
     if (counters[kCtrEvict] == 0) return;
+    if (select_pass_is_void(t, shift)) return;
     const long long k = st->k;
     const int32_t c = st->hist[threadIdx.x];
     const int32_t excl = block_exclusive_scan<256>(c, warp_sums);
@@ -546,7 +555,12 @@ move_rows_kernel(const cebag_table t, const int32_t* __restrict__ rows, const in
                 if (t.host_state && t.cache_state) t.cache_state[slot] = t.host_state[row];
                 t.slot2row[slot] = row;
                 t.row2slot[row] = slot;
-                if (t.freq) t.freq[slot] = freq_init ? freq_init[j] : 0;
+                if (t.freq) {
+                    t.freq[slot] = freq_init ? freq_init[j] : 0;
+                    if (freq_init && freq_init[j] > t.dev_state[CEBAG_STATE_MAXFREQ])
+                        atomicMax(reinterpret_cast<unsigned long long*>(t.dev_state + CEBAG_STATE_MAXFREQ),
+                                  (unsigned long long)freq_init[j]);
+                }
             } else {
                 if (t.host_state && t.cache_state) t.host_state[row] = t.cache_state[slot];
                 t.slot2row[slot] = -1;
@@ -589,6 +603,7 @@ flush_kernel(const cebag_table t, int32_t* __restrict__ counters) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         t.dev_state[CEBAG_STATE_AVAIL] = t.cache_rows;
         t.dev_state[CEBAG_STATE_EPOCH] = 0;
+        t.dev_state[CEBAG_STATE_MAXFREQ] = 0;
     }
 }
 
@@ -638,9 +653,22 @@ lfu_count_kernel(const cebag_table t, const int32_t* __restrict__ counters, cons
             }
         }
         __syncthreads();
+        unsigned long long biggest = 0ull;
         for (int e = threadIdx.x; e < kLfuTable; e += kThreads) {
-            if (s_cnt[e]) atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s_key[e]), (unsigned long long)s_cnt[e]);
+            if (s_cnt[e]) {
+                const unsigned long long add = (unsigned long long)s_cnt[e];
+                const unsigned long long now = atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s_key[e]), add) + add;
+                biggest = now > biggest ? now : biggest;
+            }
         }
+        // keep the bound of the victim selection current (one atomic per warp and tile)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, biggest, d);
+            biggest = o > biggest ? o : biggest;
+        }
+        if (lane == 0 && biggest > (unsigned long long)t.dev_state[CEBAG_STATE_MAXFREQ])
+            atomicMax(reinterpret_cast<unsigned long long*>(t.dev_state + CEBAG_STATE_MAXFREQ), biggest);
         __syncthreads();
     }
 }
@@ -843,7 +871,7 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         const int top = lfu ? 56 : 24;
         for (int shift = top; shift >= 0; shift -= 8) {
             select_hist_kernel<<<sgrid, kThreads, 0, stream>>>(*t, counters, sel, shift, shift == top);
-            select_choose_kernel<<<1, 256, 0, stream>>>(counters, sel, shift);
+            select_choose_kernel<<<1, 256, 0, stream>>>(*t, counters, sel, shift);
         }
         CEBAG_LAUNCH_CHECK();
         if (lfu) {   // ties at the threshold go to the lowest slots

@@ -126,3 +126,39 @@ extern "C" int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi,
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }
+
+// ---- stream-ordered barrier over peer memory -----------------------------------------------------------------------------
+// Every rank owns an array of CEBAG_MAX_PEERS 32-bit flags that all peers have mapped (CUDA IPC).  Round `seq`: rank r
+// stores seq into flags_of_peer[j][r] for every j (a release store over NVLink), then waits until its own flags[j] >= seq
+// for every j.  One CTA, one thread per peer: ~3 us, no NCCL call and no host involvement, so the fused exchange's two
+// barriers per step cost two tiny kernels.  A peer that never arrives trips the timeout instead of hanging the GPU.
+namespace cebag {
+namespace {
+__global__ void peer_barrier_kernel(cebag_exchange x, int rank, uint32_t seq, long long timeout_cycles, int32_t* failed) {
+    const int j = threadIdx.x;
+    if (j >= x.world) return;
+    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(x.peer[rank]);
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(x.peer[j]);
+    __threadfence_system();                                   // my earlier stores (pooled rows) are visible first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(theirs + rank), "r"(seq) : "memory");
+    const long long t0 = clock64();
+    while ((int32_t)(mine[j] - seq) < 0) {
+        if (clock64() - t0 > timeout_cycles) { *failed = 1; break; }
+    }
+    __threadfence_system();
+}
+}  // namespace
+}  // namespace cebag
+
+extern "C" int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t seq, int32_t* failed_flag,
+                                  void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(flags != nullptr && failed_flag != nullptr, "barrier arguments");
+    CEBAG_REQUIRE(flags->world >= 1 && flags->world <= CEBAG_MAX_PEERS && rank >= 0 && rank < flags->world, "barrier ranks");
+    for (int q = 0; q < flags->world; ++q) CEBAG_REQUIRE(flags->peer[q] != nullptr, "barrier flag pointer");
+    count_launches(1);
+    // ~4 s at 1.9 GHz: far beyond any skew between ranks of one step, short of the driver's watchdogs
+    cebag::peer_barrier_kernel<<<1, 32, 0, stream>>>(*flags, rank, seq, 8000000000LL, failed_flag);
+    CEBAG_LAUNCH_CHECK();
+    return CEBAG_OK;
+}

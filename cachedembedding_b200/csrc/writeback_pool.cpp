@@ -94,6 +94,8 @@ struct Pool {
         const char* d = getenv("CEBAG_WB_DELAY_US");      // test hook: a slow write-back exposes ordering bugs
         const int delay_us = (d && *d) ? atoi(d) : 0;
         if (delay_us > 0) usleep(delay_us);
+        const char* sk = getenv("CEBAG_WB_SKIP");         // probe hook: measure the DMA alone (tables end up wrong)
+        if (sk && *sk == '1') return;
         if (n <= 0) return;
         std::unique_lock<std::mutex> lock(mu);
         job = &j;

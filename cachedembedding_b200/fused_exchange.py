@@ -17,6 +17,7 @@ stores and before the backward's loads.  Buffers are plain cudaMalloc memory own
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -39,7 +40,7 @@ class _DevicePtr:
 class PeerBuffer:
     """fp32 buffer of `numel` floats on every rank of `group`, each mapped into every other rank's address space."""
 
-    def __init__(self, numel: int, group=None):
+    def __init__(self, numel: int, group=None, zero: bool = False):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -49,6 +50,9 @@ class PeerBuffer:
         ptr = ctypes.c_void_p()
         _lib.check(self.lib.cebag_device_alloc(ctypes.byref(ptr), max(self.numel, 4) * 4))
         self.local_ptr = ptr.value
+        if zero:
+            self.tensor((max(self.numel, 4),)).zero_()
+            torch.cuda.synchronize()
         handle = ctypes.create_string_buffer(64)
         _lib.check(self.lib.cebag_ipc_export(self.local_ptr, handle))
         handles: List[Optional[bytes]] = [None] * self.world
@@ -91,14 +95,22 @@ class FusedExchange:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.lib = _lib.load()
         self.B, self.F, self.D = int(global_batch), int(total_features), int(dim)
         self.feature_offset = int(feature_offset)
         self.strides = split_sizes(self.B, self.world)
         rows_max = max(self.strides)
         self.out_buf = PeerBuffer(rows_max * self.F * self.D, group)
         self.grad_buf = PeerBuffer(rows_max * self.F * self.D, group)
-        self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._forward_pending = False      # a forward whose backward has not run yet
+        # barrier over peer memory: one uint32 flag per peer on every rank (zeroed before anybody can write into it)
+        self.flag_buf = PeerBuffer(_lib.MAX_PEERS, group, zero=True)
+        self._xf = self._struct(self.flag_buf)
+        self._barrier_seq = 0
+        self._barrier_failed = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.use_peer_barrier = os.environ.get("CEBAG_PEER_BARRIER", "1") != "0"
         self._xo = self._struct(self.out_buf)
         self._xg = self._struct(self.grad_buf)
 
@@ -121,12 +133,24 @@ class FusedExchange:
 
     def barrier(self):
         """All ranks' work enqueued so far on their current streams is complete before anything enqueued after it
-        starts (a 4-byte all-reduce on the communicator's stream, ordered with the current stream by torch)."""
-        dist.all_reduce(self._flag, group=self.group)
+        starts.  One tiny kernel over peer memory (cebag_peer_barrier: a release store into every peer's flag array,
+        then an acquire spin on the own one); CEBAG_PEER_BARRIER=0 falls back to a 4-byte NCCL all-reduce."""
+        if not self.use_peer_barrier:
+            dist.all_reduce(self._flag, group=self.group)
+            return
+        self._barrier_seq += 1
+        _lib.check(self.lib.cebag_peer_barrier(ctypes.byref(self._xf), self.rank, self._barrier_seq,
+                                               self._barrier_failed.data_ptr(), _stream_ptr()))
+
+    def check_barriers(self):
+        """Raises if a peer ever failed to arrive at a barrier (reads one int from the device)."""
+        if int(self._barrier_failed.item()):
+            raise RuntimeError("fused exchange: a peer did not arrive at a barrier within the timeout")
 
     def close(self):
         self.out_buf.close()
         self.grad_buf.close()
+        self.flag_buf.close()
 
 
 class _FusedTablewiseFunction(torch.autograd.Function):

@@ -62,6 +62,8 @@ enum { CEBAG_LAYOUT_BAG_MAJOR = 0,     /* out[g, :]                       -- wha
 enum { CEBAG_STATE_AVAIL = 0,   /* free slots (upstream _cuda_available_row_num)                        */
        CEBAG_STATE_EPOCH = 1,   /* window stamp of the last successful prepare_ids                      */
        CEBAG_STATE_CALLS = 2,   /* prepare_ids calls that completed on the device, successful or not    */
+       CEBAG_STATE_MAXFREQ = 3, /* upper bound of the LFU counters of occupied slots (victim selection skips the
+                                   radix passes above its highest byte)                                  */
        CEBAG_STATE_WORDS = 8 };
 
 typedef struct cebag_table {
@@ -240,6 +242,12 @@ typedef struct cebag_exchange {
     int32_t reserved0;
     float*  peer[CEBAG_MAX_PEERS];
 } cebag_exchange;
+
+/* Stream-ordered barrier of the ranks of a fused exchange, over peer memory: flags->peer[j] is rank j's array of
+ * CEBAG_MAX_PEERS uint32 flags (zero-initialised, mapped into this process); `seq` counts the barriers (1, 2, ...).
+ * Everything enqueued on `stream` before the call, on every rank, is complete and visible before anything enqueued
+ * after it starts.  *failed_flag (device int32) is set if a peer does not arrive within a few seconds. */
+CEBAG_API int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t seq, int32_t* failed_flag, void* stream);
 
 /* ---- embedding bag over the slot cache (F.embedding_bag on cuda_cached_weight, A.2) --------------------------- */
 typedef struct cebag_bag_args {

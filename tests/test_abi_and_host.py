@@ -65,7 +65,8 @@ def test_struct_layouts_and_constants_match_header(tmp_path):
               "CEBAG_MAX_PEERS": _lib.MAX_PEERS, "CEBAG_LAYOUT_BAG_MAJOR": _lib.LAYOUT_BAG_MAJOR,
               "CEBAG_LAYOUT_SAMPLE_MAJOR": _lib.LAYOUT_SAMPLE_MAJOR, "CEBAG_LAYOUT_EXCHANGE": _lib.LAYOUT_EXCHANGE,
               "CEBAG_STATE_AVAIL": _lib.STATE_AVAIL, "CEBAG_STATE_EPOCH": _lib.STATE_EPOCH,
-              "CEBAG_STATE_CALLS": _lib.STATE_CALLS, "CEBAG_STATE_WORDS": _lib.STATE_WORDS}
+              "CEBAG_STATE_CALLS": _lib.STATE_CALLS, "CEBAG_STATE_MAXFREQ": _lib.STATE_MAXFREQ,
+              "CEBAG_STATE_WORDS": _lib.STATE_WORDS}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "cebag.h"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -86,6 +86,48 @@ def test_forward_offsets_variants_weights_padding(offset_dtype, include_last):
         torch.testing.assert_close(outm.cpu(), refm, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("D", [128, 16, 64, 256, 36])
+@pytest.mark.parametrize("kind", ["pooling1", "ragged", "mixed"])
+def test_forward_tma_gather(D, kind, monkeypatch):
+    """Calls large enough for the TMA row-gather kernel (bag_forward_tma.cu; D = 36 is not a multiple of 4 floats x 4 and
+    falls back to the LDG kernel): pooling factor 1 is a pure bulk-copy gather and must be BIT-EXACT; ragged tiles are
+    summed by the warp inside the same kernel; a padding index and a partial last tile are covered."""
+    ce = _mods()
+    import subprocess, sys, os
+    if os.environ.get("CEBAG_FWD_TMA") != "1":
+        # the kernel is opt-in (it is slower than the LDG kernel at 512 B rows): run this test in a child with it on
+        env = dict(os.environ, CEBAG_FWD_TMA="1")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                              f"{__file__}::test_forward_tma_gather[{kind}-{D}]"],
+                             env=env, cwd=root, capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+        return
+    gen = torch.Generator().manual_seed(D + len(kind))
+    C, G = 3000, 9973                     # G not a multiple of the 32-row tile
+    weight = torch.randn(C, D, generator=gen)
+    if kind == "pooling1":
+        slots = torch.randint(0, C, (G,), generator=gen)
+        offsets = torch.arange(G + 1)
+    elif kind == "ragged":
+        slots, offsets = make_bags(C, D, G, 5, gen)
+    else:                                 # mostly one id per bag, a few tiles with longer / empty bags
+        lens = torch.ones(G, dtype=torch.long)
+        lens[torch.randint(0, G, (60,), generator=gen)] = 3
+        lens[torch.randint(0, G, (60,), generator=gen)] = 0
+        offsets = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(lens, 0)])
+        slots = torch.randint(0, C, (int(offsets[-1]),), generator=gen)
+    for pad in (None, 7):
+        ref = torch.nn.functional.embedding_bag(slots, weight, offsets, mode="sum", include_last_offset=True,
+                                                padding_idx=pad)
+        out = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum",
+                                      padding_idx=pad)
+        if kind == "pooling1":
+            assert torch.equal(out.cpu(), ref), "a pure gather must be bit-exact"
+        else:
+            torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
 def test_forward_2d_input_and_empty():
     ce = _mods()
     gen = torch.Generator().manual_seed(9)
