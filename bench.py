@@ -165,6 +165,8 @@ def run_b200(args):
     wl = dict(WORKLOADS[args.workload])
     if args.cache_ratio > 0:
         wl["cache_ratio"] = args.cache_ratio
+    if args.prefetch > 0:
+        wl["prefetch"] = args.prefetch
     rows_all = list(wl["rows"])
     D, B, P = wl["dim"], wl["batch"], wl["prefetch"]
     column = args.parallelism == "column" and world > 1
@@ -220,7 +222,8 @@ def run_b200(args):
         counter.update(sample_ids(rows_dev, B, gen, dev))
     freq = counter.result()
     del counter
-    common = dict(sparse=True, mode="sum", include_last_offset=True, cache_ratio=wl["cache_ratio"], warmup_ratio=0.7,
+    common = dict(sparse=True, mode="sum", include_last_offset=True, cache_ratio=wl["cache_ratio"],
+                  warmup_ratio=args.warmup_ratio,
                   evict_strategy=ce.EvictionStrategy.LFU, cuda_row_num=C_loc, init_seed=SEED, fused_optimizer="sgd",
                   lr=1.0)
     if world == 1:
@@ -259,8 +262,13 @@ def run_b200(args):
     prefetcher = {"pf": ce.LookaheadPrefetcher(model) if overlap else None}
     col_hook = (lambda x: x.view(F, B, -1).transpose(0, 1)) if column else None     # recsys/models/dlrm.py:26-27
 
+    graph_step = world > 1 and not column and not args.no_fused_exchange and not args.no_graph_step
+
     def embed_step(slots):
         # table-wise: (B / W, F * D) after the exchange; column-wise: (B / W, F, D); single GPU: (F * B, D)
+        if graph_step:
+            # forward + fused backward as one CUDA-graph launch (the gradient already sits in the exchange's buffer)
+            return model.fused_step(slots, offsets)
         out = model(slots, offsets, shape_hook=col_hook) if column else model(slots, offsets)
         out.backward(grad_holder["g"])
         return out
@@ -351,21 +359,22 @@ def run_b200(args):
     # warm-up is rounded to whole windows internally only for the *slot* bookkeeping: steps W..W+K-1 are timed.
     # two untimed windows on scratch ids before anything is measured: first-touch costs of the caching allocator
     # (cross-stream buffers of the look-ahead driver) and of the lazily created streams/events
-    scratch = Runner([sample_ids(rows_dev, B, gen, dev) for _ in range(3 * P)], False)
-    scratch.run(0, 2 * P)
-    scratch.finish()
-    del scratch
-    if world > 1 and getattr(model, "_exchange", None) is not None:
+    if world > 1 and not column and not args.no_fused_exchange:
         # the "dense part" leaves its gradient where the fused backward reads it (no staging copy per step)
-        g = model._exchange.grad_tensor()
+        g = model._exchange_for(B).grad_tensor()
         g.copy_(grad_full)
         grad_holder["g"] = g
+    # three windows: every (ring buffer, batch) pair has been seen once (CUDA graphs of the multi-GPU step captured)
+    scratch = Runner([sample_ids(rows_dev, B, gen, dev) for _ in range(4 * P)], False)
+    scratch.run(0, 3 * P)
+    scratch.finish()
+    del scratch
     # clocks are sampled from the warm-up to the end of the end-to-end arm: every arm runs the same steps, and the
     # K timed steps alone are shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local) if rank == 0 else None
     value_runner = Runner(arms["value"], False)
     value_runner.run(0, W)
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + getattr(model, "graph_launches", 0)
     hist0 = len(mgr.num_miss_history)
     ms_total, _, _ = timed(value_runner, W, K)
     value_runner.finish()
@@ -373,7 +382,7 @@ def run_b200(args):
         tr = [t for t in value_runner.trace if t[0] >= W]
         for (s0, e0, h0), (s1, e1, h1) in zip(tr[:-1], tr[1:]):
             print(f"step {s1}: gpu +{e0.elapsed_time(e1):.3f} ms, host +{(h1 - h0) * 1e3:.3f} ms", file=sys.stderr)
-    gpu_launches = _lib.launch_count() - launches0
+    gpu_launches = _lib.launch_count() + getattr(model, "graph_launches", 0) - launches0
     miss_u = sum(mgr.num_miss_history[hist0:])
     hit_u = sum(mgr.num_hits_history[hist0:])
     evicted = sum(mgr.num_write_back_history[hist0:])
@@ -471,7 +480,8 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: {F} tables, {sum(rows_all):,} rows, dim {D}, batch {B}, "
-                        f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start, fused SGD lr=1",
+                        f"prefetch_num {P}, cache_ratio {wl['cache_ratio']}, LFU + id-frequency warm start "
+                        f"(warmup_ratio {args.warmup_ratio}), fused SGD lr=1",
             "lookahead": ("prepare_ids(window k+1) is enqueued on side streams right after the first step of window k "
                           "(no host wait inside prepare_ids); each timed window submits one prepare_ids, wherever the "
                           "timed region starts") if overlap else "serial (reference order)",
@@ -594,6 +604,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="criteo1tb", choices=sorted(WORKLOADS))
     ap.add_argument("--cache-ratio", type=float, default=0.0, help="override the workload's cache_ratio")
+    ap.add_argument("--prefetch", type=int, default=0, help="override the workload's look-ahead window (prefetch_num)")
+    ap.add_argument("--warmup-ratio", type=float, default=0.7, help="fraction of the slots preloaded at construction")
     ap.add_argument("--row-scale", type=int, default=0, help="divide table rows by this (0 = only if the host lacks RAM)")
     ap.add_argument("--freq-batches", type=int, default=8, help="batches counted for the id-frequency warm start")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -605,6 +617,8 @@ def main():
     ap.add_argument("--parallelism", default="table", choices=["table", "column"],
                     help="N > 1: table-wise sharding (BASELINE.json configs[3]) or the reference's default column-wise bag")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the untimed parity leg")
+    ap.add_argument("--no-graph-step", action="store_true",
+                    help="N > 1: eager forward + backward through autograd instead of the CUDA-graph operator step")
     ap.add_argument("--trace-steps", action="store_true", help="print GPU / host time between consecutive timed steps")
     ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)

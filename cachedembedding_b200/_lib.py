@@ -127,7 +127,7 @@ def _declare(lib):
     lib.cebag_ipc_export.argtypes = [c_void_p, ctypes.c_char_p]
     lib.cebag_ipc_import.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
     lib.cebag_ipc_close.argtypes = [c_void_p]
-    lib.cebag_peer_barrier.argtypes = [POINTER(Exchange), c_int32, ctypes.c_uint32, c_void_p, c_void_p]
+    lib.cebag_peer_barrier.argtypes = [POINTER(Exchange), c_int32, c_void_p, c_void_p, c_void_p]
     lib.cebag_prepare_workspace_bytes.argtypes = [POINTER(Table), c_int64]
     lib.cebag_prepare_workspace_bytes.restype = c_size_t
     lib.cebag_prepare_ids.argtypes = [POINTER(Table), c_void_p, c_int64, c_void_p, POINTER(Workspace),

@@ -446,7 +446,7 @@ class CachedParamMgr(nn.Module):
 
     # ---- A.3 prepare_ids --------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def prepare_ids(self, ids: torch.Tensor) -> torch.Tensor:
+    def prepare_ids(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Make every row that ``ids`` touches resident and return the slot of each id (int64, same order).
 
         One call covers a whole look-ahead window (reference: recsys/dlrm_main.py:259 passes the concatenation of
@@ -456,7 +456,10 @@ class CachedParamMgr(nn.Module):
         start = time.perf_counter()
         ids = ids.to(device=self.device, dtype=torch.long).contiguous().view(-1)
         n = ids.numel()
-        out = torch.empty_like(ids)
+        if out is None:
+            out = torch.empty_like(ids)
+        else:       # a caller-owned buffer (the look-ahead driver's static ring: stable addresses for CUDA graphs)
+            assert out.is_cuda and out.dtype == torch.long and out.is_contiguous() and out.numel() == n
         self._calls += 1
         if self._calls >= 2**31 - 64:                 # the window stamps are int32
             self._reset_stamps()

@@ -128,13 +128,21 @@ extern "C" int cebag_fill_uniform(float* dst, int64_t count, float lo, float hi,
 }
 
 // ---- stream-ordered barrier over peer memory -----------------------------------------------------------------------------
-// Every rank owns an array of CEBAG_MAX_PEERS 32-bit flags that all peers have mapped (CUDA IPC).  Round `seq`: rank r
-// stores seq into flags_of_peer[j][r] for every j (a release store over NVLink), then waits until its own flags[j] >= seq
+// Every rank owns an array of CEBAG_MAX_PEERS 32-bit flags that all peers have mapped (CUDA IPC).  Round `seq` (a device
+// counter that every barrier advances): rank r stores seq into flags_of_peer[j][r] for every j (a release store over NVLink), then waits until its own flags[j] >= seq
 // for every j.  One CTA, one thread per peer: ~3 us, no NCCL call and no host involvement, so the fused exchange's two
 // barriers per step cost two tiny kernels.  A peer that never arrives trips the timeout instead of hanging the GPU.
 namespace cebag {
 namespace {
-__global__ void peer_barrier_kernel(cebag_exchange x, int rank, uint32_t seq, long long timeout_cycles, int32_t* failed) {
+__global__ void peer_barrier_kernel(cebag_exchange x, int rank, uint32_t* seq_counter, long long timeout_cycles,
+                                    int32_t* failed) {
+    // the round number lives in device memory and advances with every barrier, so a captured CUDA graph that contains
+    // this kernel can be replayed (every rank executes the same sequence of barriers)
+    __shared__ uint32_t seq_s;
+    if (threadIdx.x == 0) seq_s = *seq_counter + 1u;
+    __syncthreads();
+    const uint32_t seq = seq_s;
+    if (threadIdx.x == 0) *seq_counter = seq;
     const int j = threadIdx.x;
     if (j >= x.world) return;
     volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(x.peer[rank]);
@@ -150,15 +158,15 @@ __global__ void peer_barrier_kernel(cebag_exchange x, int rank, uint32_t seq, lo
 }  // namespace
 }  // namespace cebag
 
-extern "C" int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t seq, int32_t* failed_flag,
+extern "C" int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t* seq_counter, int32_t* failed_flag,
                                   void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    CEBAG_REQUIRE(flags != nullptr && failed_flag != nullptr, "barrier arguments");
+    CEBAG_REQUIRE(flags != nullptr && failed_flag != nullptr && seq_counter != nullptr, "barrier arguments");
     CEBAG_REQUIRE(flags->world >= 1 && flags->world <= CEBAG_MAX_PEERS && rank >= 0 && rank < flags->world, "barrier ranks");
     for (int q = 0; q < flags->world; ++q) CEBAG_REQUIRE(flags->peer[q] != nullptr, "barrier flag pointer");
     count_launches(1);
     // ~4 s at 1.9 GHz: far beyond any skew between ranks of one step, short of the driver's watchdogs
-    cebag::peer_barrier_kernel<<<1, 32, 0, stream>>>(*flags, rank, seq, 8000000000LL, failed_flag);
+    cebag::peer_barrier_kernel<<<1, 32, 0, stream>>>(*flags, rank, seq_counter, 8000000000LL, failed_flag);
     CEBAG_LAUNCH_CHECK();
     return CEBAG_OK;
 }

@@ -105,10 +105,12 @@ class FusedExchange:
         dev = torch.device("cuda", torch.cuda.current_device())
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._forward_pending = False      # a forward whose backward has not run yet
+        self._out_view = self._grad_view = None
+        self._bwd_bytes = {}
         # barrier over peer memory: one uint32 flag per peer on every rank (zeroed before anybody can write into it)
         self.flag_buf = PeerBuffer(_lib.MAX_PEERS, group, zero=True)
         self._xf = self._struct(self.flag_buf)
-        self._barrier_seq = 0
+        self._barrier_seq = torch.zeros(1, dtype=torch.int32, device=dev)      # advanced on the device by every barrier
         self._barrier_failed = torch.zeros(1, dtype=torch.int32, device=dev)
         self.use_peer_barrier = os.environ.get("CEBAG_PEER_BARRIER", "1") != "0"
         self._xo = self._struct(self.out_buf)
@@ -126,10 +128,16 @@ class FusedExchange:
         return self.strides[self.rank]
 
     def out_tensor(self) -> torch.Tensor:
-        return self.out_buf.tensor((self.local_rows, self.F * self.D))
+        """This rank's (B_rank, F * D) slice of the pooled embeddings: a view of the peer-mapped output buffer (wrapping
+        foreign memory in a tensor costs ~30 us of host time, so the view is made once)."""
+        if self._out_view is None:
+            self._out_view = self.out_buf.tensor((self.local_rows, self.F * self.D))
+        return self._out_view
 
     def grad_tensor(self) -> torch.Tensor:
-        return self.grad_buf.tensor((self.local_rows, self.F * self.D))
+        if self._grad_view is None:
+            self._grad_view = self.grad_buf.tensor((self.local_rows, self.F * self.D))
+        return self._grad_view
 
     def barrier(self):
         """All ranks' work enqueued so far on their current streams is complete before anything enqueued after it
@@ -138,8 +146,7 @@ class FusedExchange:
         if not self.use_peer_barrier:
             dist.all_reduce(self._flag, group=self.group)
             return
-        self._barrier_seq += 1
-        _lib.check(self.lib.cebag_peer_barrier(ctypes.byref(self._xf), self.rank, self._barrier_seq,
+        _lib.check(self.lib.cebag_peer_barrier(ctypes.byref(self._xf), self.rank, self._barrier_seq.data_ptr(),
                                                self._barrier_failed.data_ptr(), _stream_ptr()))
 
     def check_barriers(self):
@@ -170,8 +177,8 @@ class _FusedTablewiseFunction(torch.autograd.Function):
         _lib.check(lib.cebag_bag_forward(ctypes.byref(a), None, _stream_ptr()))
         exch.barrier()                      # every rank's rows have landed in my buffer
         ctx.save_for_backward(weight, slot_ids, offsets)
-        ctx.bag, ctx.exch = bag, exch
-        return exch.out_tensor()
+        ctx.bag, ctx.exch, ctx.args = bag, exch, a
+        return exch.out_tensor().view(exch.local_rows, exch.F * exch.D)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -185,10 +192,12 @@ class _FusedTablewiseFunction(torch.autograd.Function):
         if grad_out.data_ptr() != gbuf.data_ptr():
             gbuf.copy_(grad_out.reshape(gbuf.shape))        # producers that write into grad_tensor() skip this copy
         exch.barrier()                      # every rank's gradient is in place before anyone reads it
-        a = _bag_args(weight, slot_ids, offsets, None, bag.include_last_offset, _lib.MODE_SUM, bag.padding_idx,
-                      _lib.LAYOUT_EXCHANGE, exch.B)
+        a = ctx.args                        # the forward's arguments, now pointing at the gradient buffers
         a.exchange = ctypes.pointer(exch._xg)
-        nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
+        key = (int(a.n), int(a.dim))
+        nbytes = exch._bwd_bytes.get(key)
+        if nbytes is None:
+            nbytes = exch._bwd_bytes[key] = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
         plan = bag._take_backward_plan(slot_ids, offsets, None, _lib.MODE_SUM, nbytes)
         ws = plan if plan is not None else torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
         state = bag.cache_weight_mgr.cuda_cached_state

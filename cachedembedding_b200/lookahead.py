@@ -29,8 +29,8 @@ Hazards and how they are closed:
   * slot ids (side stream) and rows (copy stream) are consumed on the compute stream: `PrefetchHandle.wait()` makes it
     wait for both completion events -- and makes the HOST wait for the call's result record, so that a window that
     does not fit the cache raises there, before any of its batches is enqueued;
-  * backward-plan buffers are a ring of two windows owned by this object: the buffers of window k-1 are reused for
-    window k+1 only after the same fence.
+  * slot-id and backward-plan buffers are rings of three windows owned by this object (stable addresses, so that a
+    step can be replayed as a CUDA graph): the buffers of window k-2 are reused for window k+1, after k-2's fence.
 Pooled sums and updated rows are unaffected by which victims are chosen (the cache is transparent); the slot maps
 follow the oracle run with the same two-window protection (tests/test_gpu_parity.py).
 """
@@ -39,6 +39,9 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
+
+
+_RING = 3     # windows whose slot ids / backward plans exist at once: w (being prepared), w-1 (computing), w-2 (draining)
 
 
 class PrefetchHandle:
@@ -86,13 +89,14 @@ class LookaheadPrefetcher:
         self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
         self.mgr._defer_results = True
-        self._plan_ring = [[], []]         # backward-plan workspaces of the even / odd windows
+        self._plan_ring = [[] for _ in range(_RING)]      # backward-plan workspaces of window w % 3
+        self._slot_ring = [None] * _RING                  # slot ids of window w % 3: stable addresses (CUDA graphs)
         self._fences = {}                  # window index -> event recorded after its compute was enqueued
         self._submitted = 0                # windows submitted since the last drain
         self._enqueued = 0                 # windows whose compute has been enqueued since the last drain
 
-    def _plan_buffer(self, parity: int, j: int, nbytes: int) -> torch.Tensor:
-        ring = self._plan_ring[parity]
+    def _plan_buffer(self, slot: int, j: int, nbytes: int) -> torch.Tensor:
+        ring = self._plan_ring[slot]
         while len(ring) <= j:
             ring.append(None)
         if ring[j] is None or ring[j].numel() < nbytes:
@@ -127,7 +131,7 @@ class LookaheadPrefetcher:
         w = self._submitted
         self._submitted += 1
         fence = self._victims_fence(w)
-        parity = w & 1
+        slot = w % _RING
         mgr._copy_stream, mgr._victims_ready = self.copy_stream, fence
         if self.copy_stream is None:
             side.wait_event(fence)
@@ -136,7 +140,15 @@ class LookaheadPrefetcher:
                 parts = ids if isinstance(ids, (list, tuple)) else [ids]
                 parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
                 ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
-                slot_ids = mgr.prepare_ids(ids_dev)
+                # the slot ids of window w live in a ring buffer that is reused for window w+3: stable addresses (a
+                # CUDA graph per (buffer, batch) can be replayed), and the readers of the old content -- the steps of
+                # window w-3 -- finished a whole window ago, so waiting for their fence costs nothing
+                ring = self._slot_ring[slot]
+                if ring is None or ring.numel() != ids_dev.numel():
+                    ring = self._slot_ring[slot] = torch.empty_like(ids_dev)
+                elif self._fences.get(w - _RING) is not None:
+                    side.wait_event(self._fences[w - _RING])
+                slot_ids = mgr.prepare_ids(ids_dev, out=ring)
                 rows_done = mgr._rows_ready
                 mgr._rows_ready = None             # the handle carries it; forward() of the bag need not wait again
                 if offsets is not None and self.bag is not None:
@@ -144,10 +156,10 @@ class LookaheadPrefetcher:
                     # path (the side stream has passed the fence by now: the plan buffers of window w-2 are free);
                     # splitting by the batches' own sizes gives the views the training loop passes to forward
                     offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
-                    self.bag.drop_backward_plans(parity)
+                    self.bag.drop_backward_plans(slot)
                     for j, (chunk, off) in enumerate(zip(torch.split(slot_ids, [t.numel() for t in parts]), offs)):
-                        self.bag.plan_backward(chunk, off, layout, layout_batch, tag=parity,
-                                               workspace_factory=lambda n, p=parity, j=j: self._plan_buffer(p, j, n))
+                        self.bag.plan_backward(chunk, off, layout, layout_batch, tag=slot,
+                                               workspace_factory=lambda n, p=slot, j=j: self._plan_buffer(p, j, n))
                 done = torch.cuda.Event()
                 done.record(side)
         finally:
@@ -162,7 +174,7 @@ class LookaheadPrefetcher:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._fences[self._enqueued] = ev
-        self._fences.pop(self._enqueued - 3, None)
+        self._fences.pop(self._enqueued - 4, None)
         self._enqueued += 1
 
     def drain(self):
@@ -186,4 +198,5 @@ class LookaheadPrefetcher:
         self.mgr._defer_results = self._saved_defer
         if self.bag is not None:
             self.bag.drop_backward_plans()
-        self._plan_ring = [[], []]
+        self._plan_ring = [[] for _ in range(_RING)]
+        self._slot_ring = [None] * _RING

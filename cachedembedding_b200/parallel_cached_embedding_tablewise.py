@@ -132,8 +132,8 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
                 and self.mode == "sum" and self._fused_optimizer is not None and batch_size >= self.world_size
                 and self.training and torch.is_grad_enabled())
 
-    def _forward_fused(self, slot_ids, offsets, batch_size):
-        from .fused_exchange import FusedExchange, _FusedTablewiseFunction
+    def _exchange_for(self, batch_size):
+        from .fused_exchange import FusedExchange
         if not hasattr(self, "_exchanges"):
             self._exchanges = {}
         exch = self._exchanges.get(batch_size)
@@ -145,6 +145,11 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
             exch = FusedExchange(batch_size, total_features, feature_offset, self.embedding_dim, self.process_group)
             self._exchanges[batch_size] = exch
         self._exchange = exch
+        return exch
+
+    def _forward_fused(self, slot_ids, offsets, batch_size):
+        from .fused_exchange import _FusedTablewiseFunction
+        exch = self._exchange_for(batch_size)
         offsets = offsets.to(slot_ids.device)
         if offsets.dtype not in (torch.int32, torch.int64):
             offsets = offsets.long()
@@ -152,6 +157,58 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         out = _FusedTablewiseFunction.apply(self.cache_weight_mgr.cuda_cached_weight, slot_ids.contiguous().view(-1),
                                             offsets.contiguous(), self, exch)
         return out
+
+    def fused_step(self, slot_ids: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        """Forward + fused backward/optimizer of one batch as ONE CUDA-graph launch (fused exchange only).
+
+        The operator step of the reference's isolation harness (benchmark/benchmark_cache.py:58-72: forward, then
+        backward of a given gradient) when the gradient of the pooled embeddings is already where the backward reads it
+        (`exchange.grad_tensor()`): gather + barrier + barrier + segment-reduce/optimizer are captured once per
+        (slot-id buffer, offsets, backward plan) and replayed, which takes the ~0.2 ms of Python / autograd / ctypes per
+        step down to one graph launch -- at 8 ranks a step is only ~0.3 ms of GPU work.  Needs cache_op off, slot ids in
+        a buffer with a stable address (the look-ahead driver's static ring) and a backward plan made for them
+        (`LookaheadPrefetcher.submit(..., offsets=...)`); anything else falls back to the eager forward + backward.
+        Returns this rank's (B_rank, F * D) pooled embeddings (a view of the exchange's output buffer)."""
+        import ctypes
+        from . import _lib
+        from .cache_mgr import _stream_ptr
+        from .cached_embedding import _bag_args
+        n_local = len(self.assigned_table_list)
+        batch_size = offsets.shape[0] // n_local
+        plan = getattr(self, "_bwd_plans", {}).get((slot_ids.data_ptr(), slot_ids.numel()))
+        if self.cache_op or plan is None or not self._use_fused_exchange(batch_size, None) or offsets.device != slot_ids.device:
+            out = self(slot_ids, offsets)
+            out.backward(self._exchange.grad_tensor() if getattr(self, "_exchange", None) is not None else torch.zeros_like(out))
+            return out
+        if not hasattr(self, "_step_graphs"):
+            self._step_graphs, self.graph_launches = {}, 0
+        exch = self._exchange_for(batch_size)
+        key = (slot_ids.data_ptr(), slot_ids.numel(), offsets.data_ptr(), plan[0].data_ptr())
+        entry = self._step_graphs.get(key)
+        self.cache_weight_mgr.wait_rows()
+        if entry is None:
+            lib = _lib.load()
+            weight = self.cache_weight_mgr.cuda_cached_weight
+            fused = self._fused_optimizer
+            state = self.cache_weight_mgr.cuda_cached_state
+            a = _bag_args(weight, slot_ids, offsets, None, self.include_last_offset, _lib.MODE_SUM, self.padding_idx,
+                          _lib.LAYOUT_EXCHANGE, exch.B)
+            nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
+            before = _lib.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                a.exchange = ctypes.pointer(exch._xo)
+                _lib.check(lib.cebag_bag_forward(ctypes.byref(a), None, _stream_ptr()))
+                exch.barrier()          # every rank's rows have landed (the consumer of the output would run here)
+                exch.barrier()          # every rank's gradient is in place
+                a.exchange = ctypes.pointer(exch._xg)
+                _lib.check(lib.cebag_bag_backward_fused(
+                    ctypes.byref(a), None, weight.data_ptr(), state.data_ptr() if state is not None else None,
+                    fused["kind"], fused["lr"], fused["eps"], plan[0].data_ptr(), nbytes, 1, _stream_ptr()))
+            entry = self._step_graphs[key] = (graph, _lib.launch_count() - before, (slot_ids, offsets, plan[0]))
+        entry[0].replay()
+        self.graph_launches += entry[1]
+        return exch.out_tensor()
 
     def split_along_rank(self, batch_size, indices: torch.Tensor, offsets: torch.Tensor = None,
                          per_sample_weights=None):

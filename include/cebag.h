@@ -244,10 +244,13 @@ typedef struct cebag_exchange {
 } cebag_exchange;
 
 /* Stream-ordered barrier of the ranks of a fused exchange, over peer memory: flags->peer[j] is rank j's array of
- * CEBAG_MAX_PEERS uint32 flags (zero-initialised, mapped into this process); `seq` counts the barriers (1, 2, ...).
+ * CEBAG_MAX_PEERS uint32 flags (zero-initialised, mapped into this process); *seq_counter (device uint32, zero at
+ * start, private to this rank) counts the barriers and is advanced by the kernel itself, so the call can be captured
+ * in a CUDA graph and replayed.
  * Everything enqueued on `stream` before the call, on every rank, is complete and visible before anything enqueued
  * after it starts.  *failed_flag (device int32) is set if a peer does not arrive within a few seconds. */
-CEBAG_API int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t seq, int32_t* failed_flag, void* stream);
+CEBAG_API int cebag_peer_barrier(const cebag_exchange* flags, int32_t rank, uint32_t* seq_counter, int32_t* failed_flag,
+                       void* stream);
 
 /* ---- embedding bag over the slot cache (F.embedding_bag on cuda_cached_weight, A.2) --------------------------- */
 typedef struct cebag_bag_args {

@@ -2,6 +2,8 @@
 for knob sweeps.  Prints per-kernel event timings from the library's own timers.
 
 usage: python scripts/profile_step.py [steps] [batch]
+       ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+           --log-file gpurun_out/launches.csv python scripts/profile_step.py 2      # launch list of the timed steps only
 """
 import os
 import sys
@@ -45,6 +47,7 @@ def main():
         out.backward(grad)
     torch.cuda.synchronize()
     _lib.profile_enable(True)
+    torch.cuda.cudart().cudaProfilerStart()       # `ncu --profile-from-start off` captures from here
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -52,6 +55,7 @@ def main():
         out.backward(grad)
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     prof = _lib.profile_collect()
     ms = e0.elapsed_time(e1) / steps
     alg = {"bag_forward": n * (8 + 4 * D) + n * 4 * D + (n + 1) * 8,

@@ -176,7 +176,48 @@ def _fused_exchange_worker(rank, world, port, results):
             h = pf.submit([v for v, _, _ in windows[w + 1]], offsets=[o for _, o, _ in windows[w + 1]])
     pf.close()
 
+    # (d) the CUDA-graph operator step (fused_step) against the eager autograd path, both under the look-ahead driver
+    # with early submission; pooling factor 1 so that every window has the same size (the graphs are REPLAYED)
+    g2 = torch.Generator().manual_seed(11)
+    F_loc = len(mine)
+    local_rows = [rows[t] for t in mine]
+    base = torch.tensor([sum(local_rows[:k]) for k in range(F_loc)]).view(F_loc, 1)
+    steps1 = []
+    for _ in range(12):
+        ids = torch.stack([(torch.rand(B, generator=g2) ** 2 * n).long().clamp_(0, n - 1) for n in local_rows]) + base
+        steps1.append((ids.view(-1).cuda(), torch.randn(B, len(rows) * D, generator=g2).split(strides, 0)[rank].cuda()))
+    off1 = torch.arange(F_loc * B + 1).cuda()
+    outs1 = {}
+    for variant in ("eager", "graph"):
+        bag = bags["d_" + variant] = make_bag(True)
+        bag.set_cache_op(False)
+        outs1[variant] = []
+        pf = ce.LookaheadPrefetcher(bag)
+        wins = [steps1[w * P:(w + 1) * P] for w in range(len(steps1) // P)]
+        h = pf.submit([v for v, _ in wins[0]], offsets=off1)
+        for w, win in enumerate(wins):
+            slots = h.wait()
+            for j, (s, (_, my_grad)) in enumerate(zip(torch.chunk(slots, P), win)):
+                if variant == "graph":
+                    bag._exchange_for(B).grad_tensor().copy_(my_grad)
+                    out = bag.fused_step(s, off1)
+                else:
+                    out = bag(s, off1)
+                    out.backward(my_grad)
+                outs1[variant].append(out.detach().clone())
+                if j == 0 and w + 1 < len(wins):
+                    h = pf.submit([v for v, _ in wins[w + 1]], offsets=off1)
+            pf.window_enqueued()
+        pf.close()
     ok = True
+    if getattr(bags["d_graph"], "graph_launches", 0) == 0 or len(bags["d_graph"]._step_graphs) >= len(steps1):
+        ok = False
+        print(f"[rank {rank}] fused_step did not replay graphs: {len(bags['d_graph']._step_graphs)} graphs, "
+              f"{getattr(bags['d_graph'], 'graph_launches', 0)} launches", flush=True)
+    for k in range(len(steps1)):
+        if not torch.equal(outs1["eager"][k], outs1["graph"][k]):
+            ok = False
+            print(f"[rank {rank}] graph step {k}: pooled outputs differ from the eager path", flush=True)
     for variant in ("fused", "lookahead"):
         for k in range(STEPS):
             # same slot assignment -> same summation grouping -> same bits.  The look-ahead driver protects two windows,
@@ -190,12 +231,15 @@ def _fused_exchange_worker(rank, world, port, results):
                       f"{(outs['nccl'][k] - outs[variant][k]).abs().max().item():.3e}", flush=True)
     for b in bags.values():
         b.cache_weight_mgr.flush()
+    if not torch.equal(bags["d_eager"].weight, bags["d_graph"].weight):
+        ok = False
+        print(f"[rank {rank}] graph step: tables differ from the eager path", flush=True)
     for variant in ("fused", "lookahead"):
         if not torch.allclose(bags["nccl"].weight, bags[variant].weight, rtol=1e-5, atol=1e-6):
             ok = False
             print(f"[rank {rank}] {variant}: tables differ, max abs diff "
                   f"{(bags['nccl'].weight - bags[variant].weight).abs().max().item():.3e}", flush=True)
-    if not all(sum(b.num_write_back_history) > 0 for b in bags.values()):
+    if not all(sum(b.num_write_back_history) > 0 for k, b in bags.items() if not k.startswith("d_")):
         ok = False
         print(f"[rank {rank}] scenario did not evict: {[sum(b.num_write_back_history) for b in bags.values()]}", flush=True)
     if torch.equal(bags["fused"].weight, torch.cat([weights[t] for t in mine])):
