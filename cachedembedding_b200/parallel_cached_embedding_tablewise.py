@@ -158,7 +158,7 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
                                             offsets.contiguous(), self, exch)
         return out
 
-    def fused_step(self, slot_ids: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    def fused_step(self, slot_ids: torch.Tensor, offsets: torch.Tensor, consumer=None) -> torch.Tensor:
         """Forward + fused backward/optimizer of one batch as ONE CUDA-graph launch (fused exchange only).
 
         The operator step of the reference's isolation harness (benchmark/benchmark_cache.py:58-72: forward, then
@@ -168,7 +168,11 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         step down to one graph launch -- at 8 ranks a step is only ~0.3 ms of GPU work.  Needs cache_op off, slot ids in
         a buffer with a stable address (the look-ahead driver's static ring) and a backward plan made for them
         (`LookaheadPrefetcher.submit(..., offsets=...)`); anything else falls back to the eager forward + backward.
-        Returns this rank's (B_rank, F * D) pooled embeddings (a view of the exchange's output buffer)."""
+        `consumer(out)`, if given, is captured between the two barriers -- where the dense part of a model reads the
+        pooled embeddings and leaves their gradient in `exchange.grad_tensor()`; it must only touch buffers with stable
+        addresses.  Returns this rank's (B_rank, F * D) pooled embeddings, a view of the exchange's output buffer: like
+        in the eager path its content is only guaranteed until the backward's barrier -- a faster peer's next forward
+        may overwrite it afterwards -- so read it inside `consumer`."""
         import ctypes
         from . import _lib
         from .cache_mgr import _stream_ptr
@@ -183,7 +187,7 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         if not hasattr(self, "_step_graphs"):
             self._step_graphs, self.graph_launches = {}, 0
         exch = self._exchange_for(batch_size)
-        key = (slot_ids.data_ptr(), slot_ids.numel(), offsets.data_ptr(), plan[0].data_ptr())
+        key = (slot_ids.data_ptr(), slot_ids.numel(), offsets.data_ptr(), plan[0].data_ptr(), id(consumer))
         entry = self._step_graphs.get(key)
         self.cache_weight_mgr.wait_rows()
         if entry is None:
@@ -199,13 +203,15 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
             with torch.cuda.graph(graph):
                 a.exchange = ctypes.pointer(exch._xo)
                 _lib.check(lib.cebag_bag_forward(ctypes.byref(a), None, _stream_ptr()))
-                exch.barrier()          # every rank's rows have landed (the consumer of the output would run here)
+                exch.barrier()          # every rank's rows have landed
+                if consumer is not None:
+                    consumer(exch.out_tensor())
                 exch.barrier()          # every rank's gradient is in place
                 a.exchange = ctypes.pointer(exch._xg)
                 _lib.check(lib.cebag_bag_backward_fused(
                     ctypes.byref(a), None, weight.data_ptr(), state.data_ptr() if state is not None else None,
                     fused["kind"], fused["lr"], fused["eps"], plan[0].data_ptr(), nbytes, 1, _stream_ptr()))
-            entry = self._step_graphs[key] = (graph, _lib.launch_count() - before, (slot_ids, offsets, plan[0]))
+            entry = self._step_graphs[key] = (graph, _lib.launch_count() - before, (slot_ids, offsets, plan[0], consumer))
         entry[0].replay()
         self.graph_launches += entry[1]
         return exch.out_tensor()

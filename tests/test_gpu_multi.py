@@ -193,18 +193,26 @@ def _fused_exchange_worker(rank, world, port, results):
         bag.set_cache_op(False)
         outs1[variant] = []
         pf = ce.LookaheadPrefetcher(bag)
+        snapshot = torch.empty(strides[rank], len(rows) * D, device="cuda")
+        grad_src = torch.empty_like(snapshot)
+        gbuf = bag._exchange_for(B).grad_tensor()
+
+        def dense_part(o):       # captured between the two barriers: reads the output, leaves the gradient for the peers
+            snapshot.copy_(o)
+            gbuf.copy_(grad_src)
         wins = [steps1[w * P:(w + 1) * P] for w in range(len(steps1) // P)]
         h = pf.submit([v for v, _ in wins[0]], offsets=off1)
         for w, win in enumerate(wins):
             slots = h.wait()
             for j, (s, (_, my_grad)) in enumerate(zip(torch.chunk(slots, P), win)):
                 if variant == "graph":
-                    bag._exchange_for(B).grad_tensor().copy_(my_grad)
-                    out = bag.fused_step(s, off1)
+                    grad_src.copy_(my_grad)
+                    bag.fused_step(s, off1, consumer=dense_part)
+                    outs1[variant].append(snapshot.clone())
                 else:
                     out = bag(s, off1)
+                    outs1[variant].append(out.detach().clone())     # before the backward's barrier lets the peers go on
                     out.backward(my_grad)
-                outs1[variant].append(out.detach().clone())
                 if j == 0 and w + 1 < len(wins):
                     h = pf.submit([v for v, _ in wins[w + 1]], offsets=off1)
             pf.window_enqueued()
