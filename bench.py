@@ -259,7 +259,9 @@ def run_b200(args):
 
     grad_holder = {"g": grad_full}
     # one look-ahead driver for the whole run: its streams and plan buffers are warmed once
-    prefetcher = {"pf": ce.LookaheadPrefetcher(model) if overlap else None}
+    # N > 1: a step is one graph launch, so the host must not wait for every window's result record (it would lose its
+    # lead over the GPU); the device-side verdict still protects the table and a rejected window raises one window later
+    prefetcher = {"pf": ce.LookaheadPrefetcher(model, deferred_errors=world > 1) if overlap else None}
     col_hook = (lambda x: x.view(F, B, -1).transpose(0, 1)) if column else None     # recsys/models/dlrm.py:26-27
 
     graph_step = world > 1 and not column and not args.no_fused_exchange and not args.no_graph_step
@@ -460,6 +462,19 @@ def run_b200(args):
                 "note": ("algorithmic bytes charge a row read to every lookup (SURVEY.md 8d); a batch has only ~%d unique "
                          "rows and re-reads them from L2, so algorithmic_frac can exceed 1 -- frac is the honest one"
                          % round(u_avg))}
+    if world > 1 and not column and not args.no_fused_exchange:
+        # N > 1: the exchange is fused into these two kernels, and the rows that leave the GPU bound them -- every pooled
+        # row (forward, stores) / gradient row (backward, loads) whose sample lives on another rank crosses NVLink once
+        remote = n_b * row_b * (B - strides[rank]) / B
+        link_peak = 770.0     # measured peer-copy bandwidth per direction on this pool (B200_PROFILING.md)
+        roofline["nvlink"] = {"bytes_per_launch": int(remote), "peak": link_peak, "unit": "GB/s per direction",
+                              "peak_source": "B200_PROFILING.md (measured peer copy)"}
+        for name in ("bag_forward", "bag_backward_phase1"):
+            if name in kernels and kernels[name].get("us_per_launch"):
+                gbs = remote / (kernels[name]["us_per_launch"] / 1e6) / 1e9
+                roofline["nvlink"][name] = {"achieved": round(gbs, 1), "frac": round(gbs / link_peak, 4)}
+        roofline["note"] += ("; at N > 1 the dominant kernels are NVLink-bound (see nvlink), their HBM fraction is low by "
+                             "construction")
     # whole step against the HBM roofline: compulsory bytes of forward + backward + the sort / probe traffic
     step_bytes = compulsory["bag_forward"] + compulsory["bag_backward_phase1"] + n_b * 40 + n_b * 20
     roofline["step_hbm_frac"] = round(step_bytes / (ms_total / K / 1e3) / 1e9 / peak, 4)

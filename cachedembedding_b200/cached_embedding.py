@@ -244,6 +244,12 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
 
     def _preprocess(self, weight, cuda_row_num, ids_freq_mapping=None, warmup_ratio=0.7, buffer_size=50_000,
                     pin_weight=False, with_row_state=False):
+        width = weight.shape[1]       # the row width the kernels will see (a column shard for the column-wise bag)
+        limit = 512 if width % 4 == 0 else 128
+        if width > limit:
+            raise NotImplementedError(
+                f"rows of {width} floats are not supported: the bag kernels keep a row in the registers of one warp, up "
+                f"to 512 floats when the width is a multiple of 4 (128-bit accesses) and up to 128 floats otherwise")
         self.cache_weight_mgr = CachedParamMgr(weight, cuda_row_num, buffer_size, pin_weight,
                                                evict_strategy=self.evict_strategy, with_row_state=with_row_state)
         self.cache_weight_mgr.reorder(ids_freq_mapping, warmup_ratio)

@@ -101,6 +101,8 @@ __global__ void end_call_kernel(const cebag_table t, const int32_t* __restrict__
     if (status == CEBAG_OK) {
         t.dev_state[CEBAG_STATE_AVAIL] += E - M;
         t.dev_state[CEBAG_STATE_EPOCH] = counters[kCtrEpoch];
+        // no LFU counter can grow by more than the n lookups of the call: a cheap upper bound for the victim selection
+        if (t.freq) t.dev_state[CEBAG_STATE_MAXFREQ] += n;
     }
     t.dev_state[CEBAG_STATE_CALLS] += 1;
     if (result) {
@@ -131,7 +133,10 @@ constexpr int kProbeIds = 4;  // ids in flight per thread
 __global__ void __launch_bounds__(kThreads)
 probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, int64_t* __restrict__ out,
              int32_t* __restrict__ miss_pos, int32_t* __restrict__ counters) {
+    __shared__ int32_t cta_misses, cta_base;
     const int lane = lane_id();
+    if (threadIdx.x == 0) cta_misses = 0;
+    __syncthreads();
     const int64_t tile = (int64_t)kThreads * kProbeIds;
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
         int64_t id[kProbeIds];
@@ -152,10 +157,12 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
         if (bad) atomicOr(&counters[kCtrBadIndex], 1);
 #pragma unroll
         for (int u = 0; u < kProbeIds; ++u) slot[u] = live[u] ? t.row2slot[row[u]] : 0;
+        unsigned missed[kProbeIds];
+        int warp_misses = 0;
 #pragma unroll
         for (int u = 0; u < kProbeIds; ++u) {
-            int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
-            bool miss = live[u] && slot[u] < 0;
+            const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
+            const bool miss = live[u] && slot[u] < 0;
             const bool hit = live[u] && !miss;
             if (hit) out[i] = slot[u];
             // The slot is needed by this call.  Ids arrive feature-major: the 32 ids of a warp belong to one table, and
@@ -166,19 +173,32 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
                 uint8_t* flag = t.hit_flags + slot[u];
                 if (!*flag) *flag = 1;
             }
-            // warp-aggregated append of the positions that missed
-            unsigned m = __ballot_sync(0xffffffffu, miss);
-            if (m) {
-                int32_t basepos = 0;
-                if (lane == __ffs(m) - 1) basepos = atomicAdd(&counters[kCtrMissLookups], __popc(m));
-                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(m) - 1);
-                if (miss) {
+            missed[u] = __ballot_sync(0xffffffffu, miss);
+            warp_misses += __popc(missed[u]);
+        }
+        // Append the positions that missed: warps reserve inside the CTA (shared atomic), the CTA reserves in the list
+        // with ONE global atomic per tile -- a single hot counter otherwise serialises ~10^5 warp-level atomics.
+        int32_t warp_off = 0;
+        if (warp_misses && lane == 0) warp_off = atomicAdd(&cta_misses, warp_misses);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cta_base = cta_misses ? atomicAdd(&counters[kCtrMissLookups], cta_misses) : 0;
+            cta_misses = 0;
+        }
+        __syncthreads();
+        if (warp_misses) {
+            int32_t pos = cta_base + __shfl_sync(0xffffffffu, warp_off, 0);
+#pragma unroll
+            for (int u = 0; u < kProbeIds; ++u) {
+                if ((missed[u] >> lane) & 1u) {
+                    const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
                     out[i] = -1;
-                    miss_pos[basepos + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-                    uint32_t bit = 1u << (row[u] & 31);
+                    miss_pos[pos + __popc(missed[u] & ((1u << lane) - 1u))] = (int32_t)i;
+                    const uint32_t bit = 1u << (row[u] & 31);
                     uint32_t* word = t.miss_bitmap + (row[u] >> 5);
                     if (!(*reinterpret_cast<volatile uint32_t*>(word) & bit)) atomicOr(word, bit);
                 }
+                pos += __popc(missed[u]);
             }
         }
     }
@@ -262,8 +282,8 @@ __device__ __forceinline__ bool slot_key(const cebag_table& t, int64_t s, int32_
     return true;
 }
 
-// LFU: every counter of an occupied slot is <= dev_state[MAXFREQ], so a radix pass above that value's highest byte
-// sees digit 0 everywhere and changes nothing (the counters are int64, the counts rarely need more than 3-4 bytes)
+// LFU: every counter of an occupied slot is <= dev_state[MAXFREQ] (largest warm-start count + all lookups since), so a
+// radix pass above that bound's highest byte sees digit 0 everywhere and changes nothing (the counters are int64)
 __device__ __forceinline__ bool select_pass_is_void(const cebag_table& t, int shift) {
     return t.strategy == CEBAG_EVICT_LFU && shift > 0 &&
            ((unsigned long long)t.dev_state[CEBAG_STATE_MAXFREQ] >> shift) == 0ull;
@@ -653,22 +673,9 @@ lfu_count_kernel(const cebag_table t, const int32_t* __restrict__ counters, cons
             }
         }
         __syncthreads();
-        unsigned long long biggest = 0ull;
         for (int e = threadIdx.x; e < kLfuTable; e += kThreads) {
-            if (s_cnt[e]) {
-                const unsigned long long add = (unsigned long long)s_cnt[e];
-                const unsigned long long now = atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s_key[e]), add) + add;
-                biggest = now > biggest ? now : biggest;
-            }
+            if (s_cnt[e]) atomicAdd(reinterpret_cast<unsigned long long*>(t.freq + s_key[e]), (unsigned long long)s_cnt[e]);
         }
-        // keep the bound of the victim selection current (one atomic per warp and tile)
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, biggest, d);
-            biggest = o > biggest ? o : biggest;
-        }
-        if (lane == 0 && biggest > (unsigned long long)t.dev_state[CEBAG_STATE_MAXFREQ])
-            atomicMax(reinterpret_cast<unsigned long long*>(t.dev_state + CEBAG_STATE_MAXFREQ), biggest);
         __syncthreads();
     }
 }

@@ -45,17 +45,22 @@ _RING = 3     # windows whose slot ids / backward plans exist at once: w (being 
 
 
 class PrefetchHandle:
-    def __init__(self, mgr, slot_ids: torch.Tensor, done: torch.cuda.Event, rows_done: Optional[torch.cuda.Event]):
+    def __init__(self, mgr, slot_ids: torch.Tensor, done: torch.cuda.Event, rows_done: Optional[torch.cuda.Event],
+                 deferred_errors: bool = False):
         self._mgr = mgr
         self._slot_ids = slot_ids
         self._done = done
         self._rows_done = rows_done
+        self._deferred = deferred_errors
 
     def wait(self) -> torch.Tensor:
         """Slot ids of the window.  The host waits for the result record of the call (a few bytes written by its last
         map kernel; raises CacheCapacityError / IndexError if the device rejected the window); the current stream
-        waits, on the device, for the slot ids and for the missed rows."""
-        self._mgr._harvest()
+        waits, on the device, for the slot ids and for the missed rows.
+        With `deferred_errors` the host does not wait: records that are already there are read, and a rejected window
+        raises from a later wait() / drain() (its slot ids are -1, which forward and backward skip, and the table is
+        untouched) -- the host keeps its lead over the GPU, which matters when a step is only a graph launch."""
+        self._mgr._harvest(block=not self._deferred)
         cur = torch.cuda.current_stream()
         cur.wait_event(self._done)
         if self._rows_done is not None:
@@ -79,12 +84,13 @@ class LookaheadPrefetcher:
     (Submitting after `window_enqueued()` -- the round-1 order -- still works; it just starts the overlap later.)
     """
 
-    def __init__(self, bag_or_mgr, priority: int = -1, copy_stream: bool = True):
+    def __init__(self, bag_or_mgr, priority: int = -1, copy_stream: bool = True, deferred_errors: bool = False):
         self.bag = bag_or_mgr if hasattr(bag_or_mgr, "cache_weight_mgr") else None
         self.mgr = getattr(bag_or_mgr, "cache_weight_mgr", bag_or_mgr)
         self.device = self.mgr.device
         self.stream = torch.cuda.Stream(device=self.device, priority=priority)
         self.copy_stream = torch.cuda.Stream(device=self.device, priority=priority) if copy_stream else None
+        self.deferred_errors = deferred_errors
         self._saved_protect = self.mgr.protect_windows
         self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
@@ -167,7 +173,7 @@ class LookaheadPrefetcher:
         for t in parts:
             if t.is_cuda:
                 t.record_stream(side)
-        return PrefetchHandle(mgr, slot_ids, done, rows_done)
+        return PrefetchHandle(mgr, slot_ids, done, rows_done, self.deferred_errors)
 
     def window_enqueued(self):
         """Call after the forward/backward of the current window has been enqueued on the compute stream."""
