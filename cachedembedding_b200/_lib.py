@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcebag_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # cebag_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_INDEX = 0, 1, 2, 3, 4
@@ -37,6 +37,7 @@ EXPORTS = (
     "cebag_prepare_workspace_bytes", "cebag_prepare_ids", "cebag_prepare_ids_async", "cebag_prepare_result_status",
     "cebag_flush", "cebag_preload", "cebag_admit_row", "cebag_evict_slot", "cebag_available_rows",
     "cebag_bag_forward", "cebag_backward_workspace_bytes", "cebag_bag_backward_fused", "cebag_bag_backward_plan",
+    "cebag_backward_window_plan_bytes", "cebag_bag_backward_plan_window",
     "cebag_bag_backward_coo", "cebag_bag_backward_dense", "cebag_bag_backward_weights",
 )
 
@@ -100,6 +101,7 @@ class BagArgs(Structure):
         ("layout", c_int32),
         ("layout_batch", c_int64),
         ("exchange", POINTER(Exchange)),
+        ("plan_keys", c_void_p), ("plan_vals", c_void_p), ("plan_key_mask", ctypes.c_uint32), ("reserved1", ctypes.c_uint32),
     ]
 
 
@@ -146,6 +148,10 @@ def _declare(lib):
     lib.cebag_bag_backward_fused.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                              c_float, c_void_p, c_size_t, c_int32, c_void_p]
     lib.cebag_bag_backward_plan.argtypes = [POINTER(BagArgs), c_void_p, c_size_t, c_void_p]
+    lib.cebag_backward_window_plan_bytes.argtypes = [c_int64]
+    lib.cebag_backward_window_plan_bytes.restype = c_size_t
+    lib.cebag_bag_backward_plan_window.argtypes = [POINTER(BagArgs), c_int32, c_void_p, c_size_t, POINTER(c_void_p),
+                                                   POINTER(c_void_p), POINTER(ctypes.c_uint32), c_void_p]
     lib.cebag_bag_backward_coo.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]
     lib.cebag_bag_backward_dense.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.cebag_bag_backward_weights.argtypes = [POINTER(BagArgs), c_void_p, c_void_p, c_void_p]

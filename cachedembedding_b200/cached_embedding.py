@@ -51,6 +51,24 @@ def _bag_args(weight: torch.Tensor, slot_ids: torch.Tensor, offsets: torch.Tenso
     return a
 
 
+class BackwardPlan:
+    """The gradient-independent half of a batch's fused backward, made ahead of time: either a private plan inside
+    `workspace` (cebag_bag_backward_plan) or the batch's segment of a window plan (cebag_bag_backward_plan_window:
+    `keys` / `vals` / `mask` point into the window's sort workspace, `workspace` is this batch's scratch)."""
+    __slots__ = ("workspace", "nbytes", "offsets_ptr", "tag", "keep", "keys", "vals", "mask")
+
+    def __init__(self, workspace, nbytes, offsets_ptr, tag, keep, keys=None, vals=None, mask=0):
+        self.workspace, self.nbytes, self.offsets_ptr, self.tag, self.keep = workspace, nbytes, offsets_ptr, tag, keep
+        self.keys, self.vals, self.mask = keys, vals, mask
+
+    def apply(self, args) -> int:
+        """Point `args` at the plan; returns the workspace_has_plan value for cebag_bag_backward_fused."""
+        if self.keys is None:
+            return 1
+        args.plan_keys, args.plan_vals, args.plan_key_mask = self.keys, self.vals, self.mask
+        return 2
+
+
 class _CachedBagFunction(torch.autograd.Function):
     """out = embedding_bag(cache[slot_ids], offsets); backward per the owning module's backward mode."""
 
@@ -86,16 +104,18 @@ class _CachedBagFunction(torch.autograd.Function):
                 nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
                 plan = owner._take_backward_plan(slot_ids, offsets, psw, mode, nbytes) \
                     if hasattr(owner, "_take_backward_plan") else None
+                has_plan = 0
                 if plan is not None:
-                    ws = plan
+                    ws = plan.workspace
                     ws.record_stream(torch.cuda.current_stream())
+                    has_plan = plan.apply(a)
                 else:
                     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
                 state = owner.cache_weight_mgr.cuda_cached_state
                 _lib.check(lib.cebag_bag_backward_fused(
                     ctypes.byref(a), grad_out.data_ptr(), weight.data_ptr(),
                     state.data_ptr() if state is not None else None, fused["kind"], fused["lr"], fused["eps"],
-                    ws.data_ptr(), nbytes, 1 if plan is not None else 0, stream))
+                    ws.data_ptr(), nbytes, has_plan, stream))
             elif owner is not None and not owner.sparse:
                 nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
                 ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
@@ -293,7 +313,50 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         if not hasattr(self, "_bwd_plans"):
             self._bwd_plans = {}
         # the plan is only valid for these very tensors: keep them alive so that their addresses cannot be recycled
-        self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = (ws, offsets.data_ptr(), nbytes, tag, slot_ids, offsets)
+        self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = BackwardPlan(ws, nbytes, offsets.data_ptr(), tag,
+                                                                               (slot_ids, offsets))
+        return True
+
+    def plan_backward_window(self, chunks, offsets_list, layout="bag_major", layout_batch=0, window_factory=None,
+                             scratch_factory=None, tag=None) -> bool:
+        """plan_backward for all batches of a look-ahead window at once: ONE radix sort over (batch, slot) instead of
+        one per batch (cebag_bag_backward_plan_window).  `chunks[j]` are the slot ids of batch j (views of the window's
+        slot-id tensor), `offsets_list[j]` its offsets; `window_factory(nbytes)` / `scratch_factory(j, nbytes)` supply
+        recycled buffers."""
+        if self._fused_optimizer is None or self.mode != "sum" or any(c.dim() != 1 for c in chunks):
+            return False
+        lib = _lib.load()
+        weight = self.cache_weight_mgr.cuda_cached_weight
+        P = len(chunks)
+        lay = _lib.LAYOUT_SAMPLE_MAJOR if layout == "sample_major" else _lib.LAYOUT_BAG_MAJOR
+        args = (_lib.BagArgs * P)()
+        offs = []
+        for j, (chunk, off) in enumerate(zip(chunks, offsets_list)):
+            off = off.to(weight.device)
+            if off.dtype not in (torch.int32, torch.int64):
+                off = off.long()
+            off = off.contiguous()
+            offs.append(off)
+            a = _bag_args(weight, chunk, off, None, self.include_last_offset, _lib.MODE_SUM, self.padding_idx, lay,
+                          int(layout_batch))
+            ctypes.memmove(ctypes.byref(args, j * ctypes.sizeof(_lib.BagArgs)), ctypes.byref(a), ctypes.sizeof(_lib.BagArgs))
+        total = sum(int(c.numel()) for c in chunks)
+        wbytes = int(lib.cebag_backward_window_plan_bytes(total))
+        wws = window_factory(wbytes) if window_factory is not None else \
+            torch.empty(max(wbytes, 16), dtype=torch.uint8, device=weight.device)
+        keys = (ctypes.c_void_p * P)()
+        vals = (ctypes.c_void_p * P)()
+        mask = ctypes.c_uint32(0)
+        _lib.check(lib.cebag_bag_backward_plan_window(args, P, wws.data_ptr(), wbytes, keys, vals, ctypes.byref(mask),
+                                                      _stream_ptr()))
+        if not hasattr(self, "_bwd_plans"):
+            self._bwd_plans = {}
+        for j, (chunk, off) in enumerate(zip(chunks, offs)):
+            nbytes = int(lib.cebag_backward_workspace_bytes(ctypes.byref(args[j])))
+            scratch = scratch_factory(j, nbytes) if scratch_factory is not None else \
+                torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+            self._bwd_plans[(chunk.data_ptr(), chunk.numel())] = BackwardPlan(
+                scratch, nbytes, off.data_ptr(), tag, (chunk, off, wws), keys[j], vals[j], int(mask.value))
         return True
 
     def drop_backward_plans(self, tag=None):
@@ -302,7 +365,7 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         plans = getattr(self, "_bwd_plans", None)
         if not plans:
             return
-        for key in [k for k, v in plans.items() if tag is None or v[3] == tag]:
+        for key in [k for k, v in plans.items() if tag is None or v.tag == tag]:
             del plans[key]
 
     def _take_backward_plan(self, slot_ids, offsets, psw, mode, nbytes):
@@ -312,10 +375,9 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         entry = plans.pop((slot_ids.data_ptr(), slot_ids.numel()), None)
         if entry is None:
             return None
-        ws, off_ptr, planned_bytes = entry[:3]
-        if planned_bytes != nbytes or off_ptr != offsets.data_ptr():
+        if entry.nbytes != nbytes or entry.offsets_ptr != offsets.data_ptr():
             return None
-        return ws
+        return entry
 
     # ---- forward --------------------------------------------------------------------------------------------------------------
     def _embed(self, slot_ids, offsets, per_sample_weights, layout="bag_major", layout_batch=0):

@@ -37,6 +37,22 @@ __global__ void __launch_bounds__(256) bag_of_kernel(const BagParams p, int32_t*
     }
 }
 
+// window plan: the pairs of batch `batch` -- key = (batch << slot_bits) | slot, value = bag -- written where the one
+// radix sort of the whole window reads them
+__global__ void __launch_bounds__(256)
+window_pairs_kernel(const BagParams p, uint32_t batch, int slot_bits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t mask = (1u << slot_bits) - 1u;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; g < p.num_bags; g += stride) {
+        const int64_t lo = load_offset(p, g), hi = load_offset(p, g + 1);
+        for (int64_t i = lo; i < hi; ++i) {
+            keys[i] = (batch << slot_bits) | ((uint32_t)p.slot_ids[i] & mask);
+            vals[i] = (uint32_t)g;
+        }
+    }
+}
+
 // per-lookup weight for the slow path: psw[i] (sum) or 1 / (#non-padding entries of the bag) (mean)
 __global__ void __launch_bounds__(256) lookup_weight_kernel(const BagParams p, float* __restrict__ wts) {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,6 +189,10 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
     const int chunks = p.chunks;
     const VT* __restrict__ cachev = reinterpret_cast<const VT*>(up.cache);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
+    const uint32_t kmask = p.key_mask, nslots = (uint32_t)p.cache_rows;
+    // the slot of a sorted key; keys of padding entries and of invalid slot ids (-1) update nothing
+    auto slot_of = [&](uint32_t key) { return key & kmask; };
+    auto skip = [&](uint32_t slot) { return slot == pad || slot >= nslots; };
 
     for (int64_t ck = group; ck < num_chunks; ck += num_groups) {
         const int64_t start = ck * kChunk;
@@ -222,8 +242,8 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                         const bool ok = live[u] && col < chunks;
                         gr[u][c] = ok ? Vec<VT>::ld_stream(grow[u] + col) : Vec<VT>::zero();
                         // current row, needed where a run ends inside this chunk
-                        const bool need_row = ok && tail[u] && OPT != kOptDense && k[u] != pad;
-                        wr[u][c] = need_row ? Vec<VT>::ld(cachev + (int64_t)k[u] * chunks + col) : Vec<VT>::zero();
+                        const bool need_row = ok && tail[u] && OPT != kOptDense && !skip(slot_of(k[u]));
+                        wr[u][c] = need_row ? Vec<VT>::ld(cachev + (int64_t)slot_of(k[u]) * chunks + col) : Vec<VT>::zero();
                     }
                 }
 #pragma unroll
@@ -236,8 +256,8 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
                         if (first_run && open_left) {
                             store_partial<VT, LANES, CPL>(scratch, ck, 0, chunks, lane, acc);
                             flag |= kFlagOpenLeft;
-                        } else if (k[u] != pad) {
-                            apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, k[u], acc, wr[u]);
+                        } else if (!skip(slot_of(k[u]))) {
+                            apply_update<VT, LANES, CPL, OPT>(up, chunks, lane, slot_of(k[u]), acc, wr[u]);
                         }
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) acc[c] = Vec<VT>::zero();
@@ -314,8 +334,9 @@ bag_backward_phase2a_kernel(const BagParams p, const UpdateParams up, const uint
                 }
                 bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, g + 1, cend, chunks, lane, acc);
                 if (ended) {
-                    const uint32_t slot = keys[min((g + 1) * (int64_t)kChunk, p.n) - 1];
-                    if (slot != pad) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
+                    const uint32_t slot = keys[min((g + 1) * (int64_t)kChunk, p.n) - 1] & p.key_mask;
+                    if (slot != pad && slot < (uint32_t)p.cache_rows)
+                        load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
                 } else {                                   // continues into the next super-chunk
                     store_partial<VT, LANES, CPL>(scratch_s, S, 1, chunks, lane, acc);
                     sflag |= kFlagOpenRight;
@@ -341,7 +362,7 @@ bag_backward_phase2b_kernel(const BagParams p, const UpdateParams up, const uint
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
     for (int64_t S = group; S < num_super; S += num_groups) {
         if (!(flags_s[S] & kFlagOpenRight)) continue;
-        const uint32_t slot = keys[min((S + 1) * kSuper, p.n) - 1];
+        const uint32_t slot = keys[min((S + 1) * kSuper, p.n) - 1] & p.key_mask;
         VT acc[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -349,7 +370,7 @@ bag_backward_phase2b_kernel(const BagParams p, const UpdateParams up, const uint
             acc[c] = col < chunks ? Vec<VT>::ld(sv + (S * 2 + 1) * chunks + col) : Vec<VT>::zero();
         }
         chain_sum<VT, LANES, CPL>(sv, flags_s, S + 1, num_super, chunks, lane, acc);
-        if (slot != pad) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
+        if (slot != pad && slot < (uint32_t)p.cache_rows) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
     }
 }
 
@@ -481,7 +502,7 @@ int plan_sorted_backward(const cebag_bag_args* a, const BagParams& p, const BwdL
 
 template <int OPT>
 int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* target, float* state, float lr,
-                        float eps, void* workspace, size_t workspace_bytes, bool has_plan, cudaStream_t stream) {
+                        float eps, void* workspace, size_t workspace_bytes, int has_plan, cudaStream_t stream) {
     if (a->n == 0) return CEBAG_OK;
     CEBAG_REQUIRE((grad_out != nullptr || a->layout == CEBAG_LAYOUT_EXCHANGE) && target != nullptr, "grad_out / target");
     CEBAG_REQUIRE(workspace != nullptr, "workspace");
@@ -502,12 +523,20 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     unsigned char* flags_s = reinterpret_cast<unsigned char*>(ws + L.flags_s);
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
     CEBAG_REQUIRE(!has_plan || fast, "a backward plan exists only for mode sum without per-sample weights");
-    if (!has_plan) {
-        rc = plan_sorted_backward(a, p, L, ws, stream);
-        if (rc) return rc;
-    }
+    CEBAG_REQUIRE(has_plan >= 0 && has_plan <= 2, "workspace_has_plan");
     const uint32_t *keys = nullptr, *vals = nullptr;
-    radix_sort_result(a->n, key_bits_for(a->cache_rows), ws + L.sort, &keys, &vals);
+    if (has_plan == 2) {             // this batch's segment of a window plan
+        CEBAG_REQUIRE(a->plan_keys && a->plan_vals && a->plan_key_mask, "window plan pointers");
+        keys = a->plan_keys;
+        vals = a->plan_vals;
+        p.key_mask = a->plan_key_mask;
+    } else {
+        if (!has_plan) {
+            rc = plan_sorted_backward(a, p, L, ws, stream);
+            if (rc) return rc;
+        }
+        radix_sort_result(a->n, key_bits_for(a->cache_rows), ws + L.sort, &keys, &vals);
+    }
     UpdateParams up;
     up.cache = target;
     up.state = state;
@@ -575,6 +604,67 @@ extern "C" int cebag_bag_backward_plan(const cebag_bag_args* a, void* workspace,
     return plan_sorted_backward(a, p, L, reinterpret_cast<char*>(workspace), stream);
 }
 
+extern "C" size_t cebag_backward_window_plan_bytes(int64_t total_lookups) {
+    return radix_sort_workspace_bytes(total_lookups > 0 ? total_lookups : 1);
+}
+
+extern "C" int cebag_bag_backward_plan_window(const cebag_bag_args* batches, int32_t num_batches, void* window_workspace,
+                                              size_t workspace_bytes, const uint32_t** keys_out, const uint32_t** vals_out,
+                                              uint32_t* mask_out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    CEBAG_REQUIRE(batches != nullptr && num_batches >= 1 && num_batches <= 1024, "window batches");
+    CEBAG_REQUIRE(keys_out && vals_out && mask_out, "window plan outputs");
+    CEBAG_REQUIRE(window_workspace != nullptr && aligned16(window_workspace), "window workspace");
+    int64_t total = 0;
+    for (int j = 0; j < num_batches; ++j) {
+        const cebag_bag_args* a = batches + j;
+        CEBAG_REQUIRE(a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr,
+                      "a backward plan exists only for mode sum without per-sample weights");
+        CEBAG_REQUIRE(a->cache_rows == batches[0].cache_rows, "the batches of a window share one cache");
+        CEBAG_REQUIRE(a->n >= 0 && a->num_bags < ((int64_t)1 << 31), "backward size");
+        total += a->n;
+    }
+    CEBAG_REQUIRE(total < ((int64_t)1 << 30), "window size");
+    const int slot_bits = key_bits_for(batches[0].cache_rows);
+    int batch_bits = 0;
+    while ((1 << batch_bits) < num_batches) ++batch_bits;
+    CEBAG_REQUIRE(slot_bits + batch_bits <= 32, "window key width");
+    *mask_out = (uint32_t)((1ull << slot_bits) - 1ull);
+    if (total == 0) {
+        for (int j = 0; j < num_batches; ++j) keys_out[j] = vals_out[j] = nullptr;
+        return CEBAG_OK;
+    }
+    CEBAG_REQUIRE(workspace_bytes >= radix_sort_workspace_bytes(total), "window workspace too small");
+    uint32_t *keys_in = nullptr, *vals_in = nullptr;
+    radix_sort_input_buffers(total, window_workspace, &keys_in, &vals_in);
+    int64_t begin = 0;
+    {
+        KernelScope scope(kKernBagOf, stream, num_batches);
+        for (int j = 0; j < num_batches; ++j) {
+            const cebag_bag_args* a = batches + j;
+            if (a->n == 0 || a->num_bags == 0) continue;
+            RowShape rs = row_shape(a->dim, true);
+            BagParams p;
+            int rc = fill_bag_params(a, &p, rs);
+            if (rc) return rc;
+            window_pairs_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, (uint32_t)j, slot_bits, keys_in + begin,
+                                                                                 vals_in + begin);
+            begin += a->n;
+        }
+        CEBAG_LAUNCH_CHECK();
+    }
+    const uint32_t *keys = nullptr, *vals = nullptr;
+    int rc = radix_sort_u32(total, slot_bits + batch_bits, window_workspace, workspace_bytes, &keys, &vals, stream);
+    if (rc) return rc;
+    begin = 0;
+    for (int j = 0; j < num_batches; ++j) {        // the batch index is the top of the key: segments are contiguous
+        keys_out[j] = keys + begin;
+        vals_out[j] = vals + begin;
+        begin += batches[j].n;
+    }
+    return CEBAG_OK;
+}
+
 extern "C" int cebag_bag_backward_fused(const cebag_bag_args* a, const float* grad_out, float* cache_rw,
                                         float* cache_state, int32_t optimizer, float lr, float eps, void* workspace,
                                         size_t workspace_bytes, int32_t workspace_has_plan, void* stream_) {
@@ -582,11 +672,11 @@ extern "C" int cebag_bag_backward_fused(const cebag_bag_args* a, const float* gr
     CEBAG_REQUIRE(a != nullptr, "null args");
     if (optimizer == CEBAG_OPT_SGD)
         return run_sorted_backward<kOptSgd>(a, grad_out, cache_rw, nullptr, lr, 0.f, workspace, workspace_bytes,
-                                            workspace_has_plan != 0, stream);
+                                            workspace_has_plan, stream);
     if (optimizer == CEBAG_OPT_ROWWISE_ADAGRAD) {
         CEBAG_REQUIRE(cache_state != nullptr, "row-wise Adagrad needs cache_state");
         return run_sorted_backward<kOptAdagrad>(a, grad_out, cache_rw, cache_state, lr, eps, workspace,
-                                                workspace_bytes, workspace_has_plan != 0, stream);
+                                                workspace_bytes, workspace_has_plan, stream);
     }
     set_error("unknown optimizer %d", optimizer);
     return CEBAG_ERR_INVALID;
@@ -598,7 +688,7 @@ extern "C" int cebag_bag_backward_dense(const cebag_bag_args* a, const float* gr
     CEBAG_REQUIRE(a != nullptr && grad_cache != nullptr, "null args");
     CEBAG_CUDA_CHECK(cudaMemsetAsync(grad_cache, 0, (size_t)a->cache_rows * a->dim * sizeof(float), stream));
     return run_sorted_backward<kOptDense>(a, grad_out, grad_cache, nullptr, 0.f, 0.f, workspace, workspace_bytes,
-                                          false, stream);
+                                          0, stream);
 }
 
 extern "C" int cebag_bag_backward_coo(const cebag_bag_args* a, const float* grad_out, float* values, void* stream_) {

@@ -21,6 +21,7 @@ struct BagParams {
     int64_t layout_features;  // F = num_bags / B
     int32_t dim;              // D floats
     int32_t cache_rows;       // C
+    uint32_t key_mask;        // backward: slot = sorted key & key_mask (window plans carry the batch index above it)
     int32_t chunks;           // row width in VT chunks (D/4 or D)
     int32_t offsets_are_64;
     int32_t include_last;

@@ -136,6 +136,7 @@ int fill_bag_params(const cebag_bag_args* a, BagParams* p, const RowShape& rs) {
     p->padding_idx = a->padding_idx >= 0 ? a->padding_idx : -1;
     p->dim = a->dim;
     p->cache_rows = a->cache_rows;
+    p->key_mask = 0xffffffffu;
     p->chunks = rs.chunks;
     p->offsets_are_64 = a->offsets_are_64;
     p->include_last = a->include_last_offset;

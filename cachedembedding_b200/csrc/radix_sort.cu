@@ -37,8 +37,9 @@ __device__ __forceinline__ uint32_t load_key(const void* keys_in, int64_t i) {
 }
 
 // digit counts of all passes in one read of the keys: hist[p * 256 + d]
+template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-sort_histogram_kernel(const int64_t* __restrict__ slot_ids, int64_t n, int passes, int key_bits, uint32_t* __restrict__ hist) {
+sort_histogram_kernel(const KeyT* __restrict__ slot_ids, int64_t n, int passes, int key_bits, uint32_t* __restrict__ hist) {
     __shared__ uint32_t h[kMaxPasses][kDigits];
     for (int p = 0; p < passes; ++p) h[p][threadIdx.x] = 0;
     __syncthreads();
@@ -212,9 +213,12 @@ void radix_sort_result(int64_t n, int key_bits, void* workspace, const uint32_t*
     *vals_sorted = reinterpret_cast<const uint32_t*>(ws + (in_b ? L.vals_b : L.vals_a));
 }
 
-int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* workspace, size_t workspace_bytes,
-                     const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
-                     cudaStream_t stream) {
+namespace {
+
+// keys_first: int64 slot ids (first pass reads them directly) or null when the pairs already sit in the b buffers
+int radix_sort_impl(const int64_t* slot_ids, int64_t n, int key_bits, void* workspace, size_t workspace_bytes,
+                    const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
+                    cudaStream_t stream) {
     CEBAG_REQUIRE(n > 0 && n < ((int64_t)1 << 30), "radix sort size");
     CEBAG_REQUIRE(key_bits >= 1 && key_bits <= 32, "radix sort key bits");
     SortLayout L = sort_layout(n);
@@ -232,11 +236,13 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
     const int items = sort_items();
     const int tiles = (int)ceil_div(n, (int64_t)kSortThreads * items);
     const int hgrid = (int)(ceil_div(n, kHistTile) < kNumSMs * 4 ? ceil_div(n, kHistTile) : kNumSMs * 4);
-    sort_histogram_kernel<<<hgrid, kSortThreads, 0, stream>>>(slot_ids, n, passes, key_bits, hist);
+    const bool first_is_i64 = slot_ids != nullptr;
+    if (first_is_i64) sort_histogram_kernel<int64_t><<<hgrid, kSortThreads, 0, stream>>>(slot_ids, n, passes, key_bits, hist);
+    else sort_histogram_kernel<uint32_t><<<hgrid, kSortThreads, 0, stream>>>(kbuf[1], n, passes, key_bits, hist);
     sort_offsets_kernel<<<1, kSortThreads, 0, stream>>>(hist, passes);
     CEBAG_LAUNCH_CHECK();
-    const void* kin = slot_ids;
-    const uint32_t* vin = init_vals;
+    const void* kin = first_is_i64 ? static_cast<const void*>(slot_ids) : static_cast<const void*>(kbuf[1]);
+    const uint32_t* vin = first_is_i64 ? init_vals : vbuf[1];
     for (int p = 0; p < passes; ++p) {
         const int shift = p * kDigitBits;
         const int bits = key_bits - shift < kDigitBits ? key_bits - shift : kDigitBits;
@@ -246,7 +252,7 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
 #define LAUNCH_PASS(FIRST, ITEMS)                                                                                        \
         sort_onesweep_kernel<FIRST, ITEMS><<<tiles, kSortThreads, 0, stream>>>(kin, vin, n, shift, bits, hist + p * kDigits, \
                                                                                state, tickets + p, kout, vout)
-        if (p == 0) { if (items == 8) LAUNCH_PASS(true, 8); else LAUNCH_PASS(true, 16); }
+        if (p == 0 && first_is_i64) { if (items == 8) LAUNCH_PASS(true, 8); else LAUNCH_PASS(true, 16); }
         else { if (items == 8) LAUNCH_PASS(false, 8); else LAUNCH_PASS(false, 16); }
 #undef LAUNCH_PASS
         CEBAG_LAUNCH_CHECK();
@@ -256,6 +262,27 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
     *keys_sorted = reinterpret_cast<const uint32_t*>(kin);
     *vals_sorted = vin;
     return CEBAG_OK;
+}
+
+}  // namespace
+
+int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* workspace, size_t workspace_bytes,
+                     const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
+                     cudaStream_t stream) {
+    CEBAG_REQUIRE(slot_ids != nullptr, "slot ids");
+    return radix_sort_impl(slot_ids, n, key_bits, workspace, workspace_bytes, init_vals, keys_sorted, vals_sorted, stream);
+}
+
+void radix_sort_input_buffers(int64_t n, void* workspace, uint32_t** keys_in, uint32_t** vals_in) {
+    SortLayout L = sort_layout(n);
+    char* ws = reinterpret_cast<char*>(workspace);
+    *keys_in = reinterpret_cast<uint32_t*>(ws + L.keys_b);      // pass 0 reads b and writes a
+    *vals_in = reinterpret_cast<uint32_t*>(ws + L.vals_b);
+}
+
+int radix_sort_u32(int64_t n, int key_bits, void* workspace, size_t workspace_bytes, const uint32_t** keys_sorted,
+                   const uint32_t** vals_sorted, cudaStream_t stream) {
+    return radix_sort_impl(nullptr, n, key_bits, workspace, workspace_bytes, nullptr, keys_sorted, vals_sorted, stream);
 }
 
 }  // namespace cebag

@@ -13,6 +13,12 @@ int radix_sort_slots(const int64_t* slot_ids, int64_t n, int key_bits, void* wor
                      const uint32_t* init_vals, const uint32_t** keys_sorted, const uint32_t** vals_sorted,
                      cudaStream_t stream);
 
+// The same for pairs whose 32-bit keys the caller has already written: radix_sort_input_buffers gives the arrays to
+// fill (they live inside the workspace), radix_sort_u32 sorts them on the low `key_bits` bits.
+void radix_sort_input_buffers(int64_t n, void* workspace, uint32_t** keys_in, uint32_t** vals_in);
+int radix_sort_u32(int64_t n, int key_bits, void* workspace, size_t workspace_bytes, const uint32_t** keys_sorted,
+                   const uint32_t** vals_sorted, cudaStream_t stream);
+
 // Where radix_sort_slots leaves its result inside `workspace` (for callers that sort now and consume later).
 void radix_sort_result(int64_t n, int key_bits, void* workspace, const uint32_t** keys_sorted,
                        const uint32_t** vals_sorted);

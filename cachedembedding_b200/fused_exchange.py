@@ -199,9 +199,10 @@ class _FusedTablewiseFunction(torch.autograd.Function):
         if nbytes is None:
             nbytes = exch._bwd_bytes[key] = int(lib.cebag_backward_workspace_bytes(ctypes.byref(a)))
         plan = bag._take_backward_plan(slot_ids, offsets, None, _lib.MODE_SUM, nbytes)
-        ws = plan if plan is not None else torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        ws = plan.workspace if plan is not None else torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        has_plan = plan.apply(a) if plan is not None else 0
         state = bag.cache_weight_mgr.cuda_cached_state
         _lib.check(lib.cebag_bag_backward_fused(
             ctypes.byref(a), None, weight.data_ptr(), state.data_ptr() if state is not None else None,
-            fused["kind"], fused["lr"], fused["eps"], ws.data_ptr(), nbytes, 1 if plan is not None else 0, _stream_ptr()))
+            fused["kind"], fused["lr"], fused["eps"], ws.data_ptr(), nbytes, has_plan, _stream_ptr()))
         return None, None, None, None, None

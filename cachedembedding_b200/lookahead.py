@@ -91,6 +91,7 @@ class LookaheadPrefetcher:
         self.stream = torch.cuda.Stream(device=self.device, priority=priority)
         self.copy_stream = torch.cuda.Stream(device=self.device, priority=priority) if copy_stream else None
         self.deferred_errors = deferred_errors
+        self.window_plan = None            # None: one sort per window if it fits L2, else one per batch; True / False force
         self._saved_protect = self.mgr.protect_windows
         self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
@@ -163,9 +164,24 @@ class LookaheadPrefetcher:
                     # splitting by the batches' own sizes gives the views the training loop passes to forward
                     offs = offsets if isinstance(offsets, (list, tuple)) else [offsets] * len(parts)
                     self.bag.drop_backward_plans(slot)
-                    for j, (chunk, off) in enumerate(zip(torch.split(slot_ids, [t.numel() for t in parts]), offs)):
-                        self.bag.plan_backward(chunk, off, layout, layout_batch, tag=slot,
-                                               workspace_factory=lambda n, p=slot, j=j: self._plan_buffer(p, j, n))
+                    chunks = list(torch.split(slot_ids, [t.numel() for t in parts]))
+                    if self.window_plan is None:
+                        # ONE radix sort for the whole window (key = batch index above the slot id) while its four
+                        # arrays still fit the 126 MB L2; beyond that the window sort streams through HBM, which the
+                        # fwd/bwd kernels it overlaps are bound by, and the L2-resident per-batch sorts win
+                        # (Criteo-1TB on one GPU, 13.6 M lookups per window: 0.652 vs 0.625 ms per step)
+                        use_window = len(parts) > 1 and slot_ids.numel() * 16 <= 64 << 20
+                    else:
+                        use_window = bool(self.window_plan)
+                    if use_window:
+                        self.bag.plan_backward_window(
+                            chunks, offs, layout, layout_batch, tag=slot,
+                            window_factory=lambda n, p=slot: self._plan_buffer(p, len(parts), n),
+                            scratch_factory=lambda j, n, p=slot: self._plan_buffer(p, j, n))
+                    else:
+                        for j, (chunk, off) in enumerate(zip(chunks, offs)):
+                            self.bag.plan_backward(chunk, off, layout, layout_batch, tag=slot,
+                                                   workspace_factory=lambda n, p=slot, j=j: self._plan_buffer(p, j, n))
                 done = torch.cuda.Event()
                 done.record(side)
         finally:

@@ -187,7 +187,8 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
         if not hasattr(self, "_step_graphs"):
             self._step_graphs, self.graph_launches = {}, 0
         exch = self._exchange_for(batch_size)
-        key = (slot_ids.data_ptr(), slot_ids.numel(), offsets.data_ptr(), plan[0].data_ptr(), id(consumer))
+        key = (slot_ids.data_ptr(), slot_ids.numel(), offsets.data_ptr(), plan.workspace.data_ptr(), plan.keys,
+               id(consumer))
         entry = self._step_graphs.get(key)
         self.cache_weight_mgr.wait_rows()
         if entry is None:
@@ -210,8 +211,9 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
                 a.exchange = ctypes.pointer(exch._xg)
                 _lib.check(lib.cebag_bag_backward_fused(
                     ctypes.byref(a), None, weight.data_ptr(), state.data_ptr() if state is not None else None,
-                    fused["kind"], fused["lr"], fused["eps"], plan[0].data_ptr(), nbytes, 1, _stream_ptr()))
-            entry = self._step_graphs[key] = (graph, _lib.launch_count() - before, (slot_ids, offsets, plan[0], consumer))
+                    fused["kind"], fused["lr"], fused["eps"], plan.workspace.data_ptr(), nbytes, plan.apply(a),
+                    _stream_ptr()))
+            entry = self._step_graphs[key] = (graph, _lib.launch_count() - before, (slot_ids, offsets, plan, consumer))
         entry[0].replay()
         self.graph_launches += entry[1]
         return exch.out_tensor()

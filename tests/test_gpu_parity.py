@@ -575,6 +575,39 @@ def test_planned_backward_is_bitwise_identical_to_inline():
     assert torch.equal(res[0], res[1])
 
 
+def test_window_plan_is_bitwise_identical_to_inline():
+    """cebag_bag_backward_plan_window (ONE radix sort over (batch, slot) for several ragged batches, one of them empty)
+    followed by backward with workspace_has_plan = 2 gives the same bits as the inline per-batch sort."""
+    ce = _mods()
+    gen = torch.Generator().manual_seed(19)
+    N, D = 2500, 128
+    weight = torch.randn(N, D, generator=gen)
+    batches = []
+    for G in (700, 0, 1300, 257, 900):
+        ids, offsets = make_bags(N, D, G, 4, gen) if G else (torch.zeros(0, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+        batches.append((ids, offsets, torch.randn(G, D, generator=gen)))
+    res = []
+    for planned in (False, True):
+        model = ce.CachedEmbeddingBag(N, D, _weight=weight.clone(), mode="sum", include_last_offset=True, sparse=True,
+                                      cache_ratio=1.0, warmup_ratio=1.0, evict_strategy=ce.EvictionStrategy.DATASET,
+                                      fused_optimizer="sgd", lr=0.3, padding_idx=3)
+        model.set_cache_op(False)
+        slots = model.cache_weight_mgr.prepare_ids(torch.cat([b[0] for b in batches]).cuda())
+        chunks = list(torch.split(slots, [b[0].numel() for b in batches]))
+        offs = [b[1].cuda() for b in batches]
+        if planned:
+            assert model.plan_backward_window(chunks, offs)
+            assert len(model._bwd_plans) == len([c for c in chunks if c.numel()]) or len(model._bwd_plans) >= 3
+        for chunk, off, (_, _, grad) in zip(chunks, offs, batches):
+            if chunk.numel() == 0:
+                continue
+            out = model(chunk, off)
+            out.backward(grad.cuda())
+        res.append(model.cache_weight_mgr.cuda_cached_weight.detach().cpu())
+    assert torch.equal(res[0], res[1])
+    assert not torch.equal(res[0], weight)
+
+
 def test_two_window_protection_capacity_error():
     ce = _mods()
     model = ce.CachedEmbeddingBag(100, 4, cache_ratio=0.1, warmup_ratio=0.0, evict_strategy=ce.EvictionStrategy.LFU)
