@@ -22,7 +22,10 @@ namespace cebag {
 namespace {
 
 constexpr int kBwdThreads = 256;
-constexpr int kChunk = 64;        // sorted positions per group
+#ifndef CEBAG_BWD_CHUNK
+#define CEBAG_BWD_CHUNK 64
+#endif
+constexpr int kChunk = CEBAG_BWD_CHUNK;   // sorted positions per group
 constexpr int kSuperChunks = 16;  // chunks per super-chunk (phase 2a)
 
 enum : int { kOptSgd = 0, kOptAdagrad = 1, kOptDense = 2 };
@@ -280,38 +283,35 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
     }
 }
 
-// Phase 2a: one group per super-chunk of kSuperChunks chunks.  Runs that crossed chunk boundaries but end inside
-// the super-chunk are finished here; a run that enters from the left / leaves to the right leaves ONE partial per
-// super-chunk, so a slot hit by all 65536 lookups of a tiny table is a chain of 64 partials in phase 2b, not 1024.
+// Phase 2a: one group per CHUNK (round 1 walked the 16 chunks of a super-chunk with one group: in regions of
+// medium-hot slots every chunk ends in a run that crosses into the next one, and 16 dependent chains of loads made the
+// kernel 32 us of pure latency).  The group of chunk g finishes the run that starts in g and crosses its right end --
+// if it ends inside g's super-chunk -- or parks its partial for phase 2b; the group of a super-chunk's first chunk also
+// collapses the run that enters the super-chunk from the left into ONE partial, so that a slot hit by all 65536
+// lookups of a tiny table is a chain of 64 partials in phase 2b, not 1024.  flags_left[S]: OpenLeft / Whole of the
+// super-chunk (written by its first chunk's group); flags_right[S]: a run that started inside S crosses its right end
+// (written by its last chunk's group).
 template <typename VT, int LANES, int CPL, int OPT>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase2a_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
                             const float* __restrict__ scratch_c, const unsigned char* __restrict__ flags_c,
-                            int64_t num_chunks, float* __restrict__ scratch_s, unsigned char* __restrict__ flags_s,
-                            int64_t num_super) {
+                            int64_t num_chunks, float* __restrict__ scratch_s, unsigned char* __restrict__ flags_left,
+                            unsigned char* __restrict__ flags_right, int64_t num_super) {
     const int lane = threadIdx.x & (LANES - 1);
     const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
     const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch_c);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
-    for (int64_t S = group; S < num_super; S += num_groups) {
+    static_assert(kSuperChunks == 16, "one uint4 of flags per super-chunk");
+    for (int64_t g = group; g < num_chunks; g += num_groups) {
+        const int64_t S = g / kSuperChunks;
         const int64_t c0 = S * kSuperChunks;
         const int64_t cend = min(c0 + (int64_t)kSuperChunks, num_chunks);
-        unsigned char sflag = 0;
-        // the 16 chunk flags of this super-chunk in one 128-bit load (the flag array is padded to a multiple of 16)
-        static_assert(kSuperChunks == 16, "one uint4 of flags per super-chunk");
-        const uint4 fw = *reinterpret_cast<const uint4*>(flags_c + c0);
-        const unsigned fwords[4] = {fw.x, fw.y, fw.z, fw.w};
-        if ((fw.x | fw.y | fw.z | fw.w) == 0u) {          // no run crosses a chunk boundary here
-            if (lane == 0) flags_s[S] = 0;
-            continue;
-        }
-        for (int64_t g = c0; g < cend; ++g) {
-            const int gi = (int)(g - c0);
-            const unsigned char f = (unsigned char)((fwords[gi >> 2] >> ((gi & 3) * 8)) & 0xffu);
-            if (f == 0) continue;
-            if (g == c0 && (f & kFlagOpenLeft)) {         // the run that enters this super-chunk from the left
+        const unsigned char f = flags_c[g];
+        if (g == c0) {                                       // the run that enters this super-chunk from the left
+            unsigned char sflag = 0;
+            if (f & kFlagOpenLeft) {
                 VT acc[CPL];
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
@@ -321,56 +321,121 @@ bag_backward_phase2a_kernel(const BagParams p, const UpdateParams up, const uint
                 sflag |= kFlagOpenLeft;
                 if (f & kFlagWhole) {
                     bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, c0 + 1, cend, chunks, lane, acc);
-                    if (!ended) sflag |= kFlagWhole;       // one run covers the whole super-chunk and goes on
+                    if (!ended) sflag |= kFlagWhole;         // one run covers the whole super-chunk and goes on
                 }
                 store_partial<VT, LANES, CPL>(scratch_s, S, 0, chunks, lane, acc);
             }
-            if (f & kFlagOpenRight) {                      // chunk g holds the head of a run that crosses its end
-                VT acc[CPL];
+            if (lane == 0) flags_left[S] = sflag;
+        }
+        if (g == cend - 1 && lane == 0) {
+            // does a run that STARTED inside this super-chunk cross its right end?  The last chunk tells whether any run
+            // crosses (its last run is open to the right); it started inside unless every chunk is one and the same run
+            bool crossed = cend < num_chunks && (f & (kFlagOpenRight | kFlagWhole));
+            if (crossed && !(f & kFlagOpenRight)) {
+                bool all_whole = (flags_c[c0] & kFlagOpenLeft) != 0;
+                for (int64_t h = c0; h < cend && all_whole; ++h) all_whole = (flags_c[h] & kFlagWhole) != 0;
+                crossed = !all_whole;
+            }
+            flags_right[S] = crossed ? 1 : 0;
+        }
+        if (f & kFlagOpenRight) {                            // chunk g holds the head of a run that crosses its end
+            VT acc[CPL];
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    int col = lane + c * LANES;
-                    acc[c] = col < chunks ? Vec<VT>::ld(sv + (g * 2 + 1) * chunks + col) : Vec<VT>::zero();
-                }
-                bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, g + 1, cend, chunks, lane, acc);
-                if (ended) {
-                    const uint32_t slot = keys[min((g + 1) * (int64_t)kChunk, p.n) - 1] & p.key_mask;
-                    if (slot != pad && slot < (uint32_t)p.cache_rows)
-                        load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
-                } else {                                   // continues into the next super-chunk
-                    store_partial<VT, LANES, CPL>(scratch_s, S, 1, chunks, lane, acc);
-                    sflag |= kFlagOpenRight;
-                }
+            for (int c = 0; c < CPL; ++c) {
+                int col = lane + c * LANES;
+                acc[c] = col < chunks ? Vec<VT>::ld(sv + (g * 2 + 1) * chunks + col) : Vec<VT>::zero();
+            }
+            bool ended = chain_sum<VT, LANES, CPL>(sv, flags_c, g + 1, cend, chunks, lane, acc);
+            if (ended) {
+                const uint32_t slot = keys[min((g + 1) * (int64_t)kChunk, p.n) - 1] & p.key_mask;
+                if (slot != pad && slot < (uint32_t)p.cache_rows)
+                    load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
+            } else {                                         // continues into the next super-chunk
+                store_partial<VT, LANES, CPL>(scratch_s, S, 1, chunks, lane, acc);
             }
         }
-        if (lane == 0) flags_s[S] = sflag;
     }
 }
 
-// Phase 2b: one group per run that started inside a super-chunk and crossed its end.
+// Phase 2b: one CTA per run that started inside a super-chunk and crossed its end (a hot slot of a tiny table: up to 64
+// super-chunk partials).  Round 1 walked such a chain with one group, 8 loads at a time -- ~25 us of serial latency for
+// a few dozen runs.  Here the CTA's groups each take 8 consecutive partials (all loaded at once), sum them in order up
+// to the end of the run, and group 0 adds the groups' sums in order: the same result on every run, one load latency.
 template <typename VT, int LANES, int CPL, int OPT>
 __global__ void __launch_bounds__(kBwdThreads)
 bag_backward_phase2b_kernel(const BagParams p, const UpdateParams up, const uint32_t* __restrict__ keys,
-                            const float* __restrict__ scratch_s, const unsigned char* __restrict__ flags_s,
-                            int64_t num_super) {
+                            const float* __restrict__ scratch_s, const unsigned char* __restrict__ flags_left,
+                            const unsigned char* __restrict__ flags_right, int64_t num_super) {
     constexpr int64_t kSuper = (int64_t)kSuperChunks * kChunk;
+    constexpr int kGroups = kBwdThreads / LANES;
+    constexpr int kPer = 8;
+    __shared__ VT part[kGroups][LANES * CPL];
+    __shared__ int take_s[kGroups], ended_s[kGroups], done_s;
     const int lane = threadIdx.x & (LANES - 1);
-    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
-    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    const int gi = threadIdx.x / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ sv = reinterpret_cast<const VT*>(scratch_s);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
-    for (int64_t S = group; S < num_super; S += num_groups) {
-        if (!(flags_s[S] & kFlagOpenRight)) continue;
+    for (int64_t S = blockIdx.x; S < num_super; S += gridDim.x) {
+        if (!flags_right[S]) continue;                      // uniform over the CTA
         const uint32_t slot = keys[min((S + 1) * kSuper, p.n) - 1] & p.key_mask;
-        VT acc[CPL];
+        VT total[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             int col = lane + c * LANES;
-            acc[c] = col < chunks ? Vec<VT>::ld(sv + (S * 2 + 1) * chunks + col) : Vec<VT>::zero();
+            total[c] = (gi == 0 && col < chunks) ? Vec<VT>::ld(sv + (S * 2 + 1) * chunks + col) : Vec<VT>::zero();
         }
-        chain_sum<VT, LANES, CPL>(sv, flags_s, S + 1, num_super, chunks, lane, acc);
-        if (slot != pad && slot < (uint32_t)p.cache_rows) load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, acc);
+        int64_t h = S + 1;
+        bool done = h >= num_super;
+        while (!done) {
+            const int64_t base = h + (int64_t)gi * kPer;
+            int take = 0;
+            bool ended = false;
+            for (int b = 0; b < kPer && base + b < num_super; ++b) {
+                ++take;
+                if (!(flags_left[base + b] & kFlagWhole)) { ended = true; break; }
+            }
+            VT rows[kPer][CPL];
+#pragma unroll
+            for (int b = 0; b < kPer; ++b) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    int col = lane + c * LANES;
+                    rows[b][c] = (b < take && col < chunks) ? Vec<VT>::ld(sv + ((base + b) * 2) * chunks + col) : Vec<VT>::zero();
+                }
+            }
+            VT gsum[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) gsum[c] = Vec<VT>::zero();
+#pragma unroll
+            for (int b = 0; b < kPer; ++b) {
+                if (b < take) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(gsum[c], 1.f, rows[b][c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) part[gi][lane + c * LANES] = gsum[c];
+            if (lane == 0) { take_s[gi] = take; ended_s[gi] = ended ? 1 : 0; }
+            __syncthreads();
+            if (gi == 0) {
+                bool fin = false;
+                for (int q = 0; q < kGroups && !fin; ++q) {
+                    if (take_s[q] == 0) { fin = true; break; }       // ran off the end of the array
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) Vec<VT>::fma(total[c], 1.f, part[q][lane + c * LANES]);
+                    if (ended_s[q]) fin = true;
+                }
+                if (lane == 0) done_s = fin ? 1 : 0;
+            }
+            __syncthreads();
+            done = done_s != 0;
+            h += (int64_t)kGroups * kPer;
+            if (h >= num_super) done = true;
+            __syncthreads();
+        }
+        if (gi == 0 && slot != pad && slot < (uint32_t)p.cache_rows)
+            load_row_and_apply<VT, LANES, CPL, OPT>(up, chunks, lane, slot, total);
     }
 }
 
@@ -450,7 +515,7 @@ bag_backward_weights_kernel(const BagParams p, const float* __restrict__ grad_ou
 }
 
 struct BwdLayout {
-    size_t sort, bag_of, wts, scratch, flags, scratch_s, flags_s, total;
+    size_t sort, bag_of, wts, scratch, flags, scratch_s, flags_s, flags_r, total;
     int64_t num_chunks, num_super;
 };
 
@@ -468,6 +533,7 @@ BwdLayout bwd_layout(int64_t n, int dim) {
     L.flags = off; off += align((size_t)L.num_super * kSuperChunks);
     L.scratch_s = off; off += align((size_t)L.num_super * 2 * dim * 4);
     L.flags_s = off; off += align((size_t)L.num_super);
+    L.flags_r = off; off += align((size_t)L.num_super);
     L.total = off;
     return L;
 }
@@ -521,6 +587,7 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     unsigned char* flags = reinterpret_cast<unsigned char*>(ws + L.flags);
     float* scratch_s = reinterpret_cast<float*>(ws + L.scratch_s);
     unsigned char* flags_s = reinterpret_cast<unsigned char*>(ws + L.flags_s);
+    unsigned char* flags_r = reinterpret_cast<unsigned char*>(ws + L.flags_r);
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
     CEBAG_REQUIRE(!has_plan || fast, "a backward plan exists only for mode sum without per-sample weights");
     CEBAG_REQUIRE(has_plan >= 0 && has_plan <= 2, "workspace_has_plan");
@@ -563,11 +630,12 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
         }                                                                                                           \
         {                                                                                                           \
             KernelScope scope2(kKernBwdPhase2, stream, 2);                                                          \
-            int grid = grid_for(L.num_super * LANES, kBwdThreads, 8);                                               \
-            bag_backward_phase2a_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(                     \
-                p, up, keys, scratch, flags, L.num_chunks, scratch_s, flags_s, L.num_super);                        \
-            bag_backward_phase2b_kernel<VT, LANES, CPL, OPT><<<grid, kBwdThreads, 0, stream>>>(                     \
-                p, up, keys, scratch_s, flags_s, L.num_super);                                                      \
+            int grid_a = grid_for(L.num_chunks * LANES, kBwdThreads, 8);                                            \
+            int grid_b = (int)(L.num_super < (int64_t)kNumSMs * 8 ? L.num_super : (int64_t)kNumSMs * 8);            \
+            bag_backward_phase2a_kernel<VT, LANES, CPL, OPT><<<grid_a, kBwdThreads, 0, stream>>>(                   \
+                p, up, keys, scratch, flags, L.num_chunks, scratch_s, flags_s, flags_r, L.num_super);               \
+            bag_backward_phase2b_kernel<VT, LANES, CPL, OPT><<<grid_b, kBwdThreads, 0, stream>>>(                   \
+                p, up, keys, scratch_s, flags_s, flags_r, L.num_super);                                             \
         }                                                                                                           \
     } while (0)
     CEBAG_DISPATCH_ROW_SHAPE(rs, LAUNCH_BWD);
