@@ -248,7 +248,8 @@ def run_b200(args):
     overlap = not args.no_overlap
     offsets = torch.arange(n_b + 1, dtype=torch.long, device=dev)
     # three arms (timed, per-kernel replay, end-to-end) each get their own fresh windows of ids
-    arms = {a: [sample_ids(rows_dev, B, gen, dev) for _ in range(windows * P)] for a in ("value", "profile", "e2e")}
+    arm_names = ("value", "profile", "e2e")
+    arms = {a: [sample_ids(rows_dev, B, gen, dev) for _ in range(windows * P)] for a in arm_names}
     # the gradient of the pooled embeddings, fixed (benchmark_cache.py:64); for N > 1 it is what the dense part
     # returns for this rank's slice of the batch, all features
     strides = split_sizes(B, world)
@@ -281,19 +282,32 @@ def run_b200(args):
         a few dozen launches), i.e. every window's cache operation has the rest of the previous window to hide under,
         wherever the timed region starts; every timed window still submits exactly one prepare_ids."""
 
-        def __init__(self, batches, host_inputs, overlap=overlap):
+        def __init__(self, batches, host_inputs, overlap=overlap, stage_ids=None):
             self.batches, self.host, self.overlap = batches, host_inputs, overlap
-            self.w, self.slots, self.handles, self.h2d = -1, None, {}, 0
+            self.stage_ids = args.stage_ids if stage_ids is None else stage_ids
+            self.w, self.slots, self.handles, self.staged, self.h2d = -1, None, {}, {}, 0
             self.trace = []
             self.plan = dict(offsets=offsets) if not args.no_plan_side else {}
 
         def ids(self, w):
             return self.batches[w * P:(w + 1) * P]
 
+        def stage(self, w):
+            """Host ids only: their H2D copies start one window before the window's prepare_ids (own stream)."""
+            if (self.host and self.stage_ids and w not in self.staged and w not in self.handles
+                    and (w + 1) * P <= len(self.batches)):
+                self.staged[w] = prefetcher["pf"].stage(self.ids(w))
+                self.h2d += P * n_b * 8
+
         def submit(self, w):
             if w not in self.handles and (w + 1) * P <= len(self.batches):
-                self.handles[w] = prefetcher["pf"].submit(self.ids(w), **self.plan)
-                self.h2d += P * n_b * 8 if self.host else 0
+                self.stage(w)
+                if w in self.staged:
+                    src = self.staged.pop(w)
+                else:
+                    src = self.ids(w)
+                    self.h2d += P * n_b * 8 if self.host else 0
+                self.handles[w] = prefetcher["pf"].submit(src, **self.plan)
 
         def run(self, first, count):
             """Steps [first, first+count).  host inputs: ids start in pinned host memory and are copied H2D inside the
@@ -325,6 +339,7 @@ def run_b200(args):
                     d2h += D * 4
                 if self.overlap and j == 0:
                     self.submit(w + 1)
+                    self.stage(w + 2)
                 if self.overlap and j == P - 1:
                     pf.window_enqueued()
             mgr.protect_windows = saved_protect
@@ -334,6 +349,7 @@ def run_b200(args):
             if self.overlap:
                 prefetcher["pf"].drain()
                 self.handles.clear()
+                self.staged.clear()
 
     def timed(runner, first, count):
         if world > 1:
@@ -380,10 +396,38 @@ def run_b200(args):
     hist0 = len(mgr.num_miss_history)
     ms_total, _, _ = timed(value_runner, W, K)
     value_runner.finish()
-    if args.trace_steps and rank == 0:
-        tr = [t for t in value_runner.trace if t[0] >= W]
-        for (s0, e0, h0), (s1, e1, h1) in zip(tr[:-1], tr[1:]):
-            print(f"step {s1}: gpu +{e0.elapsed_time(e1):.3f} ms, host +{(h1 - h0) * 1e3:.3f} ms", file=sys.stderr)
+    # --ab: the same timed loop again under other settings (environment knobs the library reads per call, PRIORITY =
+    # stream priority of the look-ahead driver), fresh ids each, same process and box: A/B records, not the headline
+    ab = {}
+    specs = [x for x in args.ab.split(";") if x] if overlap else []
+    for rep in range(args.ab_reps if specs else 0):
+        for spec in specs:      # interleaved: box drift hits every setting alike
+            name, _, kv = spec.partition(":")
+            env = dict(x.split("=") for x in kv.split(",") if x)
+            prio = int(env.pop("PRIORITY", -1))
+            saved = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            main_pf = prefetcher["pf"]
+            prefetcher["pf"] = ce.LookaheadPrefetcher(model, priority=prio, deferred_errors=world > 1)
+            # three untimed windows first: every ring buffer of the new driver has been allocated once
+            r = Runner([sample_ids(rows_dev, B, gen, dev) for _ in range((windows + 3) * P)], False)
+            r.run(0, 3 * P + W)
+            ab.setdefault(name, {"settings": kv, "ms_per_step": []})["ms_per_step"].append(
+                round(timed(r, 3 * P + W, K)[0] / K, 4))
+            r.finish()
+            prefetcher["pf"].close()
+            prefetcher["pf"] = main_pf
+            # the main driver's settings are back in force (close() restored what it found: two-window protection)
+            mgr.protect_windows = max(2, mgr.protect_windows)
+            mgr._defer_results = True
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    for rec in ab.values():
+        xs = sorted(rec["ms_per_step"])
+        rec["median"] = xs[len(xs) // 2]
     gpu_launches = _lib.launch_count() + getattr(model, "graph_launches", 0) - launches0
     miss_u = sum(mgr.num_miss_history[hist0:])
     hit_u = sum(mgr.num_hits_history[hist0:])
@@ -401,6 +445,17 @@ def run_b200(args):
     # ---- end-to-end arm: ids come from pinned host memory, one pooled row goes back per step ---------------------
     host_batches = [b.cpu().pin_memory() for b in arms["e2e"]]
     result_host = torch.empty(D, dtype=torch.float32).pin_memory()
+    e2e_ab = None
+    if args.e2e_ab and overlap:      # both ids-H2D orders on the same box, interleaved, fresh ids (A/B record, not the headline)
+        e2e_ab = {"staged": [], "unstaged": []}
+        for rep in range(args.ab_reps):
+            for mode in ("unstaged", "staged"):
+                hb = [sample_ids(rows_dev, B, gen, dev).cpu().pin_memory() for _ in range(windows * P)]
+                r = Runner(hb, True, stage_ids=mode == "staged")
+                r.run(0, W)
+                e2e_ab[mode].append(round(timed(r, W, K)[0] / K, 4))
+                r.finish()
+                del r, hb
     e2e_runner = Runner(host_batches, True)
     e2e_runner.run(0, W)
     e2e_ms, h2d, d2h = timed(e2e_runner, W, K)
@@ -512,6 +567,9 @@ def run_b200(args):
         "kernels": kernels,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                 "ms_per_step": e2e_ms / K,
+                "ids_h2d": ("side stream, right before the window's prepare_ids" if not args.stage_ids or not overlap else
+                            "own stream, one window ahead of the window's prepare_ids (LookaheadPrefetcher.stage); every "
+                            "timed window still copies one window of ids"),
                 "note": ("ids of every batch come from pinned host memory inside the timed region; the pooled embeddings "
                          "stay in HBM by design (their consumer is the dense part of the model), one pooled row per step "
                          "is read back as the result; the D2H traffic that matters -- evicted rows going back to the "
@@ -519,6 +577,10 @@ def run_b200(args):
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }
+    if ab:
+        line["ab"] = ab
+    if e2e_ab is not None:
+        line["e2e"]["ab_ms_per_step"] = e2e_ab
     if parity is not None:
         line["parity_check"] = parity
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -629,11 +691,20 @@ def main():
                     help="auto: the reference's table->rank map where it has one, else the snake; snake: always")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: NCCL all-to-all instead of peer-memory kernels")
     ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
+    ap.add_argument("--stage-ids", action="store_true",
+                    help="end-to-end arm: copy a window's ids H2D one window earlier on their own stream "
+                         "(LookaheadPrefetcher.stage) instead of on the side stream right before its prepare_ids; "
+                         "measured SLOWER at Criteo-1TB (0.78-0.82 vs 0.58-0.65 ms per step): the early copy shares the "
+                         "PCIe read direction with the previous window's fill, which the forward waits for")
     ap.add_argument("--parallelism", default="table", choices=["table", "column"],
                     help="N > 1: table-wise sharding (BASELINE.json configs[3]) or the reference's default column-wise bag")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the untimed parity leg")
     ap.add_argument("--no-graph-step", action="store_true",
                     help="N > 1: eager forward + backward through autograd instead of the CUDA-graph operator step")
+    ap.add_argument("--ab", default="", help="'name:ENV=V,ENV2=V2;name2:PRIORITY=0' -- time the device-resident arm again "
+                                             "under these settings in the same process")
+    ap.add_argument("--ab-reps", type=int, default=3)
+    ap.add_argument("--e2e-ab", action="store_true", help="also time the end-to-end arm with the other ids-H2D order")
     ap.add_argument("--trace-steps", action="store_true", help="print GPU / host time between consecutive timed steps")
     ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")
     ap.add_argument("--reference-budget-s", type=float, default=150.0)

@@ -611,8 +611,8 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     up.eps = eps;
     up.dim = a->dim;
     // sorted positions in flight per group (tunable: CEBAG_BWD_UNROLL = 4 | 8; 8 only for one chunk per lane)
-    static const int unroll_env = env_int("CEBAG_BWD_UNROLL", 4);
-    static const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 32);
+    const int unroll_env = env_int("CEBAG_BWD_UNROLL", 4);
+    const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 32);
 #define LAUNCH_P1(VT, LANES, CPL, FAST, UNROLL)                                                                     \
     bag_backward_phase1_kernel<VT, LANES, CPL, OPT, FAST, UNROLL><<<grid, kBwdThreads, 0, stream>>>(                \
         p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks)

@@ -80,6 +80,10 @@ template <typename VT> struct Vec;
 template <> struct Vec<float4> {
     static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     static __device__ __forceinline__ float4 ld_stream(const float4* p) { return ld_stream_f4(p); }
+    // cache row for the forward gather; POLICY 0: bypass L1, 1: allocate in L1, 2: allocate and evict last
+    template <int POLICY> static __device__ __forceinline__ float4 ld_row(const float4* p) {
+        return POLICY == 0 ? ld_stream_f4(p) : POLICY == 1 ? ld_nc_f4(p) : ld_nc_keep_f4(p);
+    }
     static __device__ __forceinline__ float4 ld(const float4* p) { return ld_f4(p); }
     static __device__ __forceinline__ void st(float4* p, const float4& v) { st_f4(p, v); }
     static __device__ __forceinline__ void st_stream(float4* p, const float4& v) { st_stream_f4(p, v); }
@@ -99,6 +103,7 @@ template <> struct Vec<float4> {
 template <> struct Vec<float> {
     static __device__ __forceinline__ float zero() { return 0.f; }
     static __device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }
+    template <int POLICY> static __device__ __forceinline__ float ld_row(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ float ld(const float* p) { return *p; }
     static __device__ __forceinline__ void st(float* p, const float& v) { *p = v; }
     static __device__ __forceinline__ void st_stream(float* p, const float& v) { *p = v; }

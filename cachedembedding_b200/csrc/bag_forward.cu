@@ -25,7 +25,11 @@ __device__ __forceinline__ unsigned group_mask() {
 // >100 for the one-bag-per-group formulation (ncu: that one was issue-bound at 25 % occupancy).
 // FAST: mode sum, no per-sample weights, no padding index, bag-major output -- the reference's DLRM call; the weight,
 // count, padding and output-pointer bookkeeping compiles away.
-template <typename VT, int LANES, int CPL, int kUnroll, bool FAST>
+// LDP: L1 policy of the row loads (Vec::ld_row).  Ids arrive feature-major and the grid walks the bags in order, so at
+// any moment every SM works on the same table: the few rows of a small table are read by all warps of all SMs at the
+// same time.  Allocating them in L1 (LDP = 1) takes those reads off the L2 slices that hold the rows: 188 -> 165 us at
+// Criteo-1TB (L1 hit rate 0.8 % -> 35 %); bypassing L1 (LDP = 0, "every row is touched once") was round 1's choice.
+template <typename VT, int LANES, int CPL, int kUnroll, bool FAST, int LDP>
 __global__ void __launch_bounds__(kFwdThreads)
 bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int lane = threadIdx.x & (LANES - 1);
@@ -72,8 +76,8 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     const int col = lane + c * LANES;
-                    acc[k][c] = (sl[k] >= 0 && col < chunks) ? Vec<VT>::ld_stream(cache + (int64_t)sl[k] * chunks + col)
-                                                             : Vec<VT>::zero();
+                    acc[k][c] = (sl[k] >= 0 && col < chunks)
+                                    ? Vec<VT>::template ld_row<LDP>(cache + (int64_t)sl[k] * chunks + col) : Vec<VT>::zero();
                 }
             }
 #pragma unroll
@@ -96,7 +100,8 @@ bag_forward_kernel(const BagParams p, float* __restrict__ out) {
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) {
                             const int col = lane + c * LANES;
-                            if (col < chunks) Vec<VT>::fma(acc[k][c], w2, Vec<VT>::ld_stream(cache + s2 * chunks + col));
+                            if (col < chunks)
+                                Vec<VT>::fma(acc[k][c], w2, Vec<VT>::template ld_row<LDP>(cache + s2 * chunks + col));
                         }
                     }
                 }
@@ -190,17 +195,25 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
         int tma_rc = CEBAG_OK;
         if (bag_forward_tma_launch(a, p, out, stream, &tma_rc)) return tma_rc;
     }
-    // rows in flight per group (tunable: CEBAG_FWD_UNROLL = 4 | 8)
-    static const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
-    static const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 16);
+    // tuning knobs, read per call (an in-process sweep can compare them): rows in flight per group (4 | 8), CTAs per SM
+    // of the grid-stride launch (32: 6.4 waves of the 5 resident CTAs per SM, 157 vs 164 us with 16), L1 policy of the
+    // row loads (0 bypass, 1 allocate, 2 allocate + evict last)
+    const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
+    const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 32);
+    const int ld_policy = env_int("CEBAG_FWD_LD", 1);
     const bool fast_path = a->per_sample_weights == nullptr && a->mode == CEBAG_MODE_SUM && a->padding_idx < 0 &&
                            a->layout == CEBAG_LAYOUT_BAG_MAJOR;
 #define LAUNCH_FWD_U(VT, LANES, CPL, UNROLL)                                                             \
     do {                                                                                                 \
         int64_t groups = ceil_div(p.num_bags, LANES);                                                    \
         int grid = grid_for(groups * LANES, kFwdThreads, ctas_per_sm);                                   \
-        if (fast_path) bag_forward_kernel<VT, LANES, CPL, UNROLL, true><<<grid, kFwdThreads, 0, stream>>>(p, out);   \
-        else bag_forward_kernel<VT, LANES, CPL, UNROLL, false><<<grid, kFwdThreads, 0, stream>>>(p, out);            \
+        if (fast_path && ld_policy == 0)                                                                 \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 0><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
+        else if (fast_path && ld_policy == 2)                                                            \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 2><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
+        else if (fast_path)                                                                              \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 1><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
+        else bag_forward_kernel<VT, LANES, CPL, UNROLL, false, 1><<<grid, kFwdThreads, 0, stream>>>(p, out);        \
     } while (0)
 #define LAUNCH_FWD(VT, LANES, CPL)                                                                       \
     do {                                                                                                 \

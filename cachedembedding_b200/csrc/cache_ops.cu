@@ -52,8 +52,6 @@ struct SelectState {             // radix-select of the k smallest keys
     int hist[256];
 };
 
-__device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
-
 __device__ __forceinline__ int32_t row_of_id(const cebag_table& t, int64_t id) {
     return t.idx_map ? __ldg(t.idx_map + id) : (int32_t)id;
 }
@@ -130,9 +128,46 @@ clear_bitmap_if_rejected_kernel(const cebag_table t, const int32_t* __restrict__
 // ---- probe ---------------------------------------------------------------------------------------------------------
 constexpr int kProbeIds = 4;  // ids in flight per thread
 
+// Where the probe raises the hit flag of slot s.  The warm-up hands out slots by frequency rank and LFU keeps the hot
+// rows where they are, so the hot slots are the LOW slot numbers: with one flag byte per slot in slot order the flags
+// of the ~10^4 hottest slots -- 40 % of a Criteo window's 13.6 M lookups -- live in a few KB, i.e. in a handful of L2
+// slices, and those slices serialise the whole kernel (ncu: one slice served 11 x the average number of sectors, issue
+// slots busy 3 %).  The probe therefore writes a SPREAD copy of the flags in the call's workspace -- slot s at byte
+// (s mod L) * M + (s div L), M = ceil(C / L): neighbouring slots are M bytes apart and the hot set covers the whole
+// array -- and collect_hits_kernel moves the raised flags into the table's slot-ordered hit_flags, which is what every
+// later kernel streams through.  L = 1 is the identity layout.
+struct FlagLayout {
+    int32_t log_l;     // L = 1 << log_l
+    int32_t m;         // M
+    int64_t bytes;     // L * M, a multiple of 16
+};
+constexpr int kMaxFlagSpreadLog = 16;
+
+FlagLayout flag_layout(int64_t cache_rows, int spread) {
+    FlagLayout f;
+    f.log_l = 0;
+    while ((1 << (f.log_l + 1)) <= spread && f.log_l + 1 <= kMaxFlagSpreadLog) ++f.log_l;
+    const int64_t l = (int64_t)1 << f.log_l;
+    int64_t m = (cache_rows + l - 1) / l;
+    if (l == 1) m = (m + 15) / 16 * 16;
+    f.m = (int32_t)m;
+    f.bytes = (l * m + 15) / 16 * 16;
+    return f;
+}
+// room for any layout the knob can ask for
+size_t flag_spread_capacity(int64_t cache_rows) { return (size_t)cache_rows + ((size_t)1 << kMaxFlagSpreadLog) + 16; }
+
+__device__ __forceinline__ int64_t flag_index(int32_t slot, int log_l, int m) {
+    return (int64_t)(slot & ((1 << log_l) - 1)) * m + (slot >> log_l);
+}
+
+// MODE 0: one lane per distinct slot of the warp (match.any) checks the flag and raises it if it reads 0
+// MODE 1: every lane that hit checks its flag (the four loads of a thread are issued back to back), raises it on a 0
+// The check may read a stale 0 from L1, which only costs a store; racing stores of the same 1 are fine.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, int64_t* __restrict__ out,
-             int32_t* __restrict__ miss_pos, int32_t* __restrict__ counters) {
+             int32_t* __restrict__ miss_pos, int32_t* __restrict__ counters, uint8_t* __restrict__ flags, int log_l, int m) {
     __shared__ int32_t cta_misses, cta_base;
     const int lane = lane_id();
     if (threadIdx.x == 0) cta_misses = 0;
@@ -159,22 +194,42 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
         for (int u = 0; u < kProbeIds; ++u) slot[u] = live[u] ? t.row2slot[row[u]] : 0;
         unsigned missed[kProbeIds];
         int warp_misses = 0;
+        if (MODE == 1) {
+            bool hit[kProbeIds];
+            uint8_t* fp[kProbeIds];
+            unsigned seen[kProbeIds];
 #pragma unroll
-        for (int u = 0; u < kProbeIds; ++u) {
-            const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
-            const bool miss = live[u] && slot[u] < 0;
-            const bool hit = live[u] && !miss;
-            if (hit) out[i] = slot[u];
-            // The slot is needed by this call.  Ids arrive feature-major: the 32 ids of a warp belong to one table, and
-            // for the small tables most of them are the same few rows -- one lane per distinct slot raises the flag
-            // (racing stores of the same 1 are fine; the check may read a stale 0 from L1, which only costs a store).
-            const unsigned same = __match_any_sync(0xffffffffu, hit ? slot[u] : -1 - lane);
-            if (hit && lane == __ffs(same) - 1) {
-                uint8_t* flag = t.hit_flags + slot[u];
-                if (!*flag) *flag = 1;
+            for (int u = 0; u < kProbeIds; ++u) {
+                const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
+                const bool miss = live[u] && slot[u] < 0;
+                hit[u] = live[u] && !miss;
+                if (hit[u]) out[i] = slot[u];
+                fp[u] = flags + (hit[u] ? flag_index(slot[u], log_l, m) : 0);
+                missed[u] = __ballot_sync(0xffffffffu, miss);
+                warp_misses += __popc(missed[u]);
             }
-            missed[u] = __ballot_sync(0xffffffffu, miss);
-            warp_misses += __popc(missed[u]);
+#pragma unroll
+            for (int u = 0; u < kProbeIds; ++u) seen[u] = hit[u] ? (unsigned)*fp[u] : 1u;
+#pragma unroll
+            for (int u = 0; u < kProbeIds; ++u)
+                if (!seen[u]) *fp[u] = 1;
+        } else {
+#pragma unroll
+            for (int u = 0; u < kProbeIds; ++u) {
+                const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
+                const bool miss = live[u] && slot[u] < 0;
+                const bool hit = live[u] && !miss;
+                if (hit) out[i] = slot[u];
+                // ids arrive feature-major: the 32 ids of a warp belong to one table, and for the small tables most of
+                // them are the same few rows
+                const unsigned same = __match_any_sync(0xffffffffu, hit ? slot[u] : -1 - lane);
+                if (hit && lane == __ffs(same) - 1) {
+                    uint8_t* flag = flags + flag_index(slot[u], log_l, m);
+                    if (!*flag) *flag = 1;
+                }
+                missed[u] = __ballot_sync(0xffffffffu, miss);
+                warp_misses += __popc(missed[u]);
+            }
         }
         // Append the positions that missed: warps reserve inside the CTA (shared atomic), the CTA reserves in the list
         // with ONE global atomic per tile -- a single hot counter otherwise serialises ~10^5 warp-level atomics.
@@ -204,15 +259,29 @@ probe_kernel(const cebag_table t, const int64_t* __restrict__ ids, int64_t n, in
     }
 }
 
-// unique hits of the call = raised hit flags (16 slots per 128-bit load; the flag array is padded to 16)
+// The raised flags of the spread array go to the table's slot-ordered hit_flags (all-zero before); their number is the
+// call's count of unique hits.  16 flags per 128-bit load.
 __global__ void __launch_bounds__(kThreads)
-count_hits_kernel(const cebag_table t, int32_t* __restrict__ counters) {
-    const int64_t vecs = ceil_div_dev(t.cache_rows, 16);
-    const uint4* flags = reinterpret_cast<const uint4*>(t.hit_flags);
+collect_hits_kernel(const cebag_table t, const uint8_t* __restrict__ flags, int64_t vecs, int log_l, int m,
+                    int32_t* __restrict__ counters) {
+    const uint4* f16 = reinterpret_cast<const uint4*>(flags);
     int32_t c = 0;
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < vecs; v += (int64_t)gridDim.x * kThreads) {
-        const uint4 f = flags[v];
-        c += __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w);     // flags are 0 or 1
+        const uint4 f = f16[v];
+        if (!(f.x | f.y | f.z | f.w)) continue;
+        const uint32_t w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if ((w[k] >> (8 * b)) & 0xffu) {
+                    const int64_t idx = v * 16 + k * 4 + b;
+                    const int64_t slot = ((idx % m) << log_l) | (idx / m);
+                    t.hit_flags[slot] = 1;
+                    ++c;
+                }
+            }
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
@@ -681,7 +750,8 @@ lfu_count_kernel(const cebag_table t, const int32_t* __restrict__ counters, cons
 }
 
 struct PrepLayout {
-    size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, fill_src, total;
+    size_t counters, select, miss_pos, miss_rows, free_slots, victim_rows, flags_a, flags_b, bitmap_sums, scan_ws, fill_src,
+           spread_flags, total;
     int64_t bitmap_blocks, words, hit_words;
 };
 
@@ -707,6 +777,7 @@ PrepLayout prep_layout(const cebag_table* t, int64_t n) {
     int64_t longest = C > L.bitmap_blocks ? C : L.bitmap_blocks;
     L.scan_ws = off; off += align(scan_workspace_bytes(longest));
     L.fill_src = off; off += align((size_t)C * 4);
+    L.spread_flags = off; off += align(flag_spread_capacity(C));
     L.miss_pos = off; off += align((size_t)nn * 4);
     L.total = off;
     return L;
@@ -842,15 +913,29 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         count_launches(1);
         CEBAG_LAUNCH_CHECK();
     }
-    const int sgrid = grid_for(C, kThreads, 8);
+    // CTAs per SM of the map kernels (read per call).  They are latency-bound and, under the look-ahead driver, run next
+    // to the bandwidth-bound forward / backward of the previous window, whose SM slots they take: narrow grids cost
+    // the side stream time it has and give the compute stream time it needs.
+    const int prep_ctas = env_int("CEBAG_PREP_CTAS_PER_SM", 8);
+    const int sgrid = grid_for(C, kThreads, prep_ctas);
     const bool lfu = t->strategy == CEBAG_EVICT_LFU;
 
     {
         KernelScope scope(kKernProbe, stream, 3);
         begin_call_kernel<<<1, 32, 0, stream>>>(*t, counters);
-        probe_kernel<<<grid_for(ceil_div(n, kProbeIds), kThreads, 8), kThreads, 0, stream>>>(*t, ids, n, slot_ids_out,
-                                                                                            miss_pos, counters);
-        count_hits_kernel<<<grid_for(ceil_div(C, 16), kThreads, 8), kThreads, 0, stream>>>(*t, counters);
+        // tuning knobs, read per call (a call is ~40 launches; lets one process compare settings)
+        const int probe_mode = env_int("CEBAG_PROBE_MODE", 1);
+        const int probe_ctas = env_int("CEBAG_PROBE_CTAS_PER_SM", prep_ctas);
+        const FlagLayout fl = flag_layout(C, env_int("CEBAG_FLAG_SPREAD", 4096));
+        uint8_t* spread = reinterpret_cast<uint8_t*>(base + L.spread_flags);
+        CEBAG_CUDA_CHECK(cudaMemsetAsync(spread, 0, (size_t)fl.bytes, stream));
+        const int pgrid = grid_for(ceil_div(n, kProbeIds), kThreads, probe_ctas);
+        if (probe_mode == 1)
+            probe_kernel<1><<<pgrid, kThreads, 0, stream>>>(*t, ids, n, slot_ids_out, miss_pos, counters, spread, fl.log_l, fl.m);
+        else
+            probe_kernel<0><<<pgrid, kThreads, 0, stream>>>(*t, ids, n, slot_ids_out, miss_pos, counters, spread, fl.log_l, fl.m);
+        collect_hits_kernel<<<grid_for(fl.bytes / 16, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, spread, fl.bytes / 16, fl.log_l,
+                                                                                          fl.m, counters);
         CEBAG_LAUNCH_CHECK();
     }
     {   // missed rows, ascending: count, then (after the verdict) emit
@@ -897,25 +982,25 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         rc = exclusive_scan_inplace(flags_b, C, nullptr, scan_ws, stream);
         if (rc) return rc;
         emit_free_slots_kernel<<<sgrid, kThreads, 0, stream>>>(counters, flags_a, flags_b, C, free_slots);
-        commit_admission_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, miss_rows,
+        commit_admission_kernel<<<grid_for(admit_bound, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, miss_rows,
                                                                                             free_slots, victim_rows, fill_src);
-        stamp_hits_kernel<<<grid_for(L.hit_words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.hit_words);
+        stamp_hits_kernel<<<grid_for(L.hit_words, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, L.hit_words);
         CEBAG_LAUNCH_CHECK();
     }
     {   // everything that only needs the maps: slot ids of the ids that missed, LFU counts, the result record
         KernelScope scope(kKernFixup, stream);
-        fixup_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, stream>>>(*t, counters, ids, miss_pos, slot_ids_out);
+        fixup_kernel<<<grid_for(n, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, ids, miss_pos, slot_ids_out);
         CEBAG_LAUNCH_CHECK();
     }
     if (lfu) {
         KernelScope scope(kKernLfuCount, stream);
-        lfu_count_kernel<<<grid_for(ceil_div(n, kLfuTile) * kThreads, kThreads, 8), kThreads, 0, stream>>>(
+        lfu_count_kernel<<<grid_for(ceil_div(n, kLfuTile) * kThreads, kThreads, prep_ctas), kThreads, 0, stream>>>(
             *t, counters, slot_ids_out, n);
         CEBAG_LAUNCH_CHECK();
     }
     {   // victims in ascending host-row order (flags_a) and the slots that still hold them (flags_b)
         KernelScope scope(kKernVictimRank, stream, 6);
-        mark_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, victim_rows);
+        mark_victims_kernel<<<grid_for(admit_bound, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, victim_rows);
         bitmap_count_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
                                                                                counters + kCtrEvict);
         CEBAG_LAUNCH_CHECK();
@@ -923,9 +1008,9 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
         if (rc) return rc;
         bitmap_emit_kernel<<<(int)L.bitmap_blocks, kScanThreads, 0, stream>>>(t->miss_bitmap, L.words, bitmap_sums,
                                                                               flags_a, C, counters + kCtrEvict);
-        resolve_victims_kernel<<<grid_for(admit_bound, kThreads, 8), kThreads, 0, stream>>>(*t, counters, flags_a, flags_b,
+        resolve_victims_kernel<<<grid_for(admit_bound, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, flags_a, flags_b,
                                                                                             dma ? ws->stage_rows : 0);
-        clear_bitmap_if_rejected_kernel<<<grid_for(L.words, kThreads, 8), kThreads, 0, stream>>>(*t, counters, L.words);
+        clear_bitmap_if_rejected_kernel<<<grid_for(L.words, kThreads, prep_ctas), kThreads, 0, stream>>>(*t, counters, L.words);
         end_call_kernel<<<1, 32, 0, stream>>>(*t, counters, n, result_dev);
         CEBAG_LAUNCH_CHECK();
     }
@@ -934,8 +1019,8 @@ extern "C" int cebag_prepare_ids_async(const cebag_table* t, const int64_t* ids,
     // PCIe-bound: ~50 GB/s x ~2 us of latency is ~110 KB in flight, a few hundred rows.  A SMALL grid matters: under
     // the look-ahead driver these kernels run next to the fwd/bwd kernels, and measured step time falls from 0.71 to
     // 0.60 ms going from 296 to 37 CTAs of 128 threads (a pure gather still reaches 46 of 51 GB/s).
-    static const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
-    static const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
+    const int swap_ctas = env_int("CEBAG_SWAP_CTAS", 56);
+    const int swap_threads = env_int("CEBAG_SWAP_THREADS", 128);
     RowLists lists;
     lists.miss_rows = miss_rows;
     lists.free_slots = free_slots;

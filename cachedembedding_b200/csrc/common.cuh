@@ -49,6 +49,19 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// read-only path WITH L1 allocation: rows that many warps of an SM read again (the hot rows of small tables)
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_nc_keep_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 // plain (coherent) 128-bit load for data that this kernel also writes
 __device__ __forceinline__ float4 ld_f4(const float4* p) {
     float4 v;

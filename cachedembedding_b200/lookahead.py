@@ -14,6 +14,10 @@ timers end in torch.cuda.synchronize()).  Here three stre
   DMA stream     : the parked victims go D2H as ONE contiguous copy-engine transfer into a pinned ring, in parallel
                    with the fill, and host threads scatter them into the table (cache_mgr.dma_writeback); a row that
                    is missed again while its write-back is in flight is filled from the staging buffer
+  ids stream     : `stage()` -- the H2D copy of a window's ids from (pinned) host memory, one window further ahead than
+                   its prepare_ids: at Criteo-1TB a window is 109 MB of int64 ids = 2 ms of PCIe, and the chain
+                   ids H2D -> map work -> fill of one window no longer fits under the previous window's compute when
+                   all three run back to back on the side stream
 
 prepare_ids never waits for the GPU (cebag_prepare_ids_async), so `submit` costs the host a few dozen kernel launches
 and may be called anywhere inside window k -- the earlier the better: right after the window's first step has been
@@ -69,6 +73,16 @@ class PrefetchHandle:
         return self._slot_ids
 
 
+class StagedIds:
+    """Ids of one window on their way to the device (LookaheadPrefetcher.stage): `tensor` is the concatenation of the
+    window's batches in a ring buffer owned by the driver, `sizes` the batches' lengths, `ready` the event recorded
+    after the last H2D copy; `done` is set by submit() (the ring buffer is recycled after it)."""
+
+    def __init__(self, tensor: torch.Tensor, sizes, ready: torch.cuda.Event):
+        self.tensor, self.sizes, self.ready = tensor, list(sizes), ready
+        self.done: Optional[torch.cuda.Event] = None
+
+
 class LookaheadPrefetcher:
     """
     pf = LookaheadPrefetcher(bag)
@@ -82,6 +96,8 @@ class LookaheadPrefetcher:
         pf.window_enqueued()
     pf.close()
     (Submitting after `window_enqueued()` -- the round-1 order -- still works; it just starts the overlap later.)
+    Ids that start in host memory can be sent ahead with `staged = pf.stage(ids_of_window_k_plus_2)` (own stream, no
+    effect on the cache) and handed to `pf.submit(staged)` one window later.
     """
 
     def __init__(self, bag_or_mgr, priority: int = -1, copy_stream: bool = True, deferred_errors: bool = False):
@@ -98,6 +114,9 @@ class LookaheadPrefetcher:
         self.mgr._defer_results = True
         self._plan_ring = [[] for _ in range(_RING)]      # backward-plan workspaces of window w % 3
         self._slot_ring = [None] * _RING                  # slot ids of window w % 3: stable addresses (CUDA graphs)
+        self._ids_stream = None                           # H2D copies of stage()
+        self._ids_ring = [None] * _RING                   # the last StagedIds of every ring buffer
+        self._staged = 0
         self._fences = {}                  # window index -> event recorded after its compute was enqueued
         self._submitted = 0                # windows submitted since the last drain
         self._enqueued = 0                 # windows whose compute has been enqueued since the last drain
@@ -121,6 +140,39 @@ class LookaheadPrefetcher:
             ev.record(torch.cuda.current_stream(self.device))
         return ev
 
+    def stage(self, ids) -> StagedIds:
+        """Start the H2D copies of a window's ids (a tensor or the list of the window's batches, normally in pinned host
+        memory) on the driver's ids stream and return at once.  Nothing of the cache is touched: call it as early as
+        the host has the batches -- one window before `submit(staged)` is what it takes to get the copy out of the
+        window's critical chain.  The device buffer is one of three ring buffers; it is recycled once the submit that
+        consumed its previous content has finished on the side stream."""
+        parts = ids if isinstance(ids, (list, tuple)) else [ids]
+        sizes = [t.numel() for t in parts]
+        total = sum(sizes)
+        if self._ids_stream is None:
+            self._ids_stream = torch.cuda.Stream(device=self.device)
+        h2d = self._ids_stream
+        k = self._staged % _RING
+        self._staged += 1
+        prev = self._ids_ring[k]
+        with torch.cuda.stream(h2d):
+            if prev is not None and prev.done is not None and prev.tensor.numel() == total:
+                h2d.wait_event(prev.done)            # the readers of the old content: that window's prepare_ids
+                buf = prev.tensor
+            else:
+                # first lap, another window size, or a staged window that was never submitted: a fresh buffer (the old
+                # one goes back to the allocator, which holds it until the side stream has passed -- record_stream)
+                buf = torch.empty(total, dtype=torch.long, device=self.device)
+            off = 0
+            for t, n in zip(parts, sizes):
+                buf[off:off + n].copy_(t.reshape(-1), non_blocking=True)
+                off += n
+            ready = torch.cuda.Event()
+            ready.record(h2d)
+        staged = StagedIds(buf, sizes, ready)
+        self._ids_ring[k] = staged
+        return staged
+
     def submit(self, ids, ready: Optional[torch.cuda.Event] = None, offsets=None, layout="bag_major",
                layout_batch=0) -> PrefetchHandle:
         """Enqueue prepare_ids(ids) on the side stream.  `ids` is a tensor or a list of tensors (the batches of the
@@ -133,6 +185,10 @@ class LookaheadPrefetcher:
         current stream already holds the window that this call is supposed to overlap)."""
         side = self.stream
         mgr = self.mgr
+        staged = ids if isinstance(ids, StagedIds) else None
+        if staged is not None:
+            side.wait_event(staged.ready)
+            staged.tensor.record_stream(side)
         if ready is not None:
             side.wait_event(ready)
         w = self._submitted
@@ -144,9 +200,13 @@ class LookaheadPrefetcher:
             side.wait_event(fence)
         try:
             with torch.cuda.stream(side):
-                parts = ids if isinstance(ids, (list, tuple)) else [ids]
-                parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
-                ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
+                if staged is not None:
+                    parts = list(torch.split(staged.tensor, staged.sizes))
+                    ids_dev = staged.tensor
+                else:
+                    parts = ids if isinstance(ids, (list, tuple)) else [ids]
+                    parts_dev = [t.to(self.device, non_blocking=True) for t in parts]
+                    ids_dev = parts_dev[0] if len(parts_dev) == 1 else torch.cat(parts_dev)
                 # the slot ids of window w live in a ring buffer that is reused for window w+3: stable addresses (a
                 # CUDA graph per (buffer, batch) can be replayed), and the readers of the old content -- the steps of
                 # window w-3 -- finished a whole window ago, so waiting for their fence costs nothing
@@ -186,9 +246,12 @@ class LookaheadPrefetcher:
                 done.record(side)
         finally:
             mgr._copy_stream, mgr._victims_ready = None, None
-        for t in parts:
-            if t.is_cuda:
-                t.record_stream(side)
+        if staged is not None:
+            staged.done = done
+        else:
+            for t in parts:
+                if t.is_cuda:
+                    t.record_stream(side)
         return PrefetchHandle(mgr, slot_ids, done, rows_done, self.deferred_errors)
 
     def window_enqueued(self):
@@ -202,6 +265,8 @@ class LookaheadPrefetcher:
     def drain(self):
         """Wait for everything submitted so far -- side stream, copy stream and the compute the fences stand for; the
         driver stays usable (streams, plan buffers and protection kept)."""
+        if self._ids_stream is not None:
+            self._ids_stream.synchronize()
         self.stream.synchronize()
         if self.copy_stream is not None:
             self.copy_stream.synchronize()
@@ -222,3 +287,4 @@ class LookaheadPrefetcher:
             self.bag.drop_backward_plans()
         self._plan_ring = [[] for _ in range(_RING)]
         self._slot_ring = [None] * _RING
+        self._ids_ring = [None] * _RING

@@ -1,7 +1,7 @@
 """Forward + fused backward of one Criteo-1TB-shape batch on a device-only slot cache (no host table), for ncu and
 for knob sweeps.  Prints per-kernel event timings from the library's own timers.
 
-usage: python scripts/profile_step.py [steps] [batch]
+usage: python scripts/profile_step.py [steps] [batch] ["name:ENV=V,..;name2:..."]   (settings the library reads per call)
        ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
            --log-file gpurun_out/launches.csv python scripts/profile_step.py 2      # launch list of the timed steps only
 """
@@ -46,25 +46,36 @@ def main():
         out = ce.embedding_bag_cached(weight, batches[i], offsets, include_last_offset=True, mode="sum", owner=owner)
         out.backward(grad)
     torch.cuda.synchronize()
-    _lib.profile_enable(True)
-    torch.cuda.cudart().cudaProfilerStart()       # `ncu --profile-from-start off` captures from here
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        out = ce.embedding_bag_cached(weight, batches[3 + i], offsets, include_last_offset=True, mode="sum", owner=owner)
-        out.backward(grad)
-    e1.record()
-    torch.cuda.synchronize()
-    torch.cuda.cudart().cudaProfilerStop()
-    prof = _lib.profile_collect()
-    ms = e0.elapsed_time(e1) / steps
+    sweep = [x for x in (sys.argv[3] if len(sys.argv) > 3 else "default:").split(";") if x]
     alg = {"bag_forward": n * (8 + 4 * D) + n * 4 * D + (n + 1) * 8,
            "bag_backward_phase1": n * 4 * D + uniq * 8 * D + n * 8}
-    knobs = {k: v for k, v in os.environ.items() if k.startswith("CEBAG_")}
-    print(f"n={n} unique={uniq} step={ms:.3f} ms  {n / ms / 1e6:.2f} G lookups/s  knobs={knobs}")
-    for name, (t, c) in prof.items():
-        extra = f"  {alg[name] / (t / c / 1e3) / 1e9:7.0f} GB/s" if name in alg else ""
-        print(f"  {name:22s} {t / steps * 1e3:8.1f} us/step{extra}")
+    comp = {"bag_forward": n * 8 + (n + 1) * 8 + uniq * 4 * D + n * 4 * D,
+            "bag_backward_phase1": n * 4 * D + uniq * 8 * D + n * 8}
+    for spec in sweep:
+        name, _, kv = spec.partition(":")
+        env = dict(x.split("=") for x in kv.split(",") if x)
+        os.environ.update(env)
+        _lib.profile_enable(True)
+        torch.cuda.cudart().cudaProfilerStart()       # `ncu --profile-from-start off` captures from here
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            out = ce.embedding_bag_cached(weight, batches[3 + i], offsets, include_last_offset=True, mode="sum", owner=owner)
+            out.backward(grad)
+        e1.record()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+        for key in env:
+            os.environ.pop(key, None)
+        ms = e0.elapsed_time(e1) / steps
+        knobs = {k: v for k, v in os.environ.items() if k.startswith("CEBAG_")}
+        print(f"[{name}] {kv} n={n} unique={uniq} step={ms:.3f} ms  {n / ms / 1e6:.2f} G lookups/s  env={knobs}")
+        for nm, (t, c) in prof.items():
+            extra = (f"  {comp[nm] / (t / c / 1e3) / 1e9:7.0f} GB/s compulsory  {alg[nm] / (t / c / 1e3) / 1e9:7.0f} GB/s algorithmic"
+                     if nm in alg else "")
+            print(f"  {nm:22s} {t / steps * 1e3:8.1f} us/step{extra}")
 
 
 if __name__ == "__main__":

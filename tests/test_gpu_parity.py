@@ -64,6 +64,32 @@ def test_forward_matches_oracle(D, mode):
     torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("D", [128, 16, 64, 256, 512, 8])
+@pytest.mark.parametrize("knobs", [{"CEBAG_FWD_LD": "0"}, {"CEBAG_FWD_LD": "2"}, {"CEBAG_FWD_UNROLL": "8"},
+                                   {"CEBAG_FWD_CTAS_PER_SM": "2", "CEBAG_FWD_LD": "0"}])
+@pytest.mark.parametrize("kind", ["pooling1", "ragged"])
+def test_forward_kernel_variants(D, knobs, kind, monkeypatch):
+    """The fast-path variants of the forward (L1 policy of the row loads, rows in flight, grid size; the library reads
+    these knobs per call) against torch: a pure gather (pooling factor 1, the DLRM call) bit for bit, ragged bags
+    within 1e-5."""
+    ce = _mods()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    gen = torch.Generator().manual_seed(D + len(kind))
+    C, G = 500, 256 * 9 + 77
+    weight = torch.randn(C, D, generator=gen)
+    if kind == "pooling1":
+        slots, offsets = torch.randint(0, C, (G,), generator=gen), torch.arange(G + 1)
+    else:
+        slots, offsets = make_bags(C, D, G, 5, gen)
+    ref = torch.nn.functional.embedding_bag(slots, weight, offsets, mode="sum", include_last_offset=True)
+    out = ce.embedding_bag_cached(weight.cuda(), slots.cuda(), offsets.cuda(), include_last_offset=True, mode="sum")
+    if kind == "pooling1":
+        assert torch.equal(out.cpu(), ref)
+    else:
+        torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("offset_dtype", [torch.int32, torch.int64])
 @pytest.mark.parametrize("include_last", [True, False])
 def test_forward_offsets_variants_weights_padding(offset_dtype, include_last):
@@ -484,14 +510,16 @@ def test_module_surface():
 # ---------------------------------------------------------------------------------------------------- look-ahead overlap
 @pytest.mark.parametrize("strategy", ["LFU", "DATASET"])
 @pytest.mark.parametrize("early,stage_rows,dma", [(True, 0, True), (False, 0, True), (True, 7, True), (True, 0, False),
-                                                   (True, 0, "slow")])
+                                                   (True, 0, "slow"), ("staged", 0, True)])
 def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy, early, stage_rows, dma, monkeypatch):
     """prepare_ids of window k+1 on a side stream while window k trains: slot ids and maps bit-exact against the
     oracle run with the same two-window protection; pooled sums / final table within 1e-5 of it.
     early: window k+1 is submitted right after the FIRST step of window k (the order bench.py uses), otherwise after its
     last step.  stage_rows = 7: most victims do not fit the staging buffer and are written back straight from their
     slots before the fill.  dma: parked victims leave through the copy engine + host threads ("slow": every host
-    scatter is delayed by 20 ms, so rows that are missed again are served from the staging buffer or not at all)."""
+    scatter is delayed by 20 ms, so rows that are missed again are served from the staging buffer or not at all).
+    early = "staged": the ids of window k+2 leave pinned host memory on the driver's ids stream (pf.stage) while window
+    k trains, and window k+1 is submitted from its staged ids (three ring buffers, each reused twice here)."""
     ce = _mods()
     if dma == "slow":
         monkeypatch.setenv("CEBAG_WB_DELAY_US", "20000")
@@ -514,7 +542,13 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     model.cache_weight_mgr.dma_writeback = bool(dma)
     pf = ce.LookaheadPrefetcher(model)
     assert model.cache_weight_mgr.protect_windows == 2
-    h = pf.submit([w.pin_memory() for w in windows[0]], offsets=offsets.cuda())   # host ids: H2D rides the side stream
+    staged = {}
+    if early == "staged":
+        pinned = [[w.pin_memory() for w in win] for win in windows]
+        staged = {0: pf.stage(pinned[0]), 1: pf.stage(pinned[1])}
+        h = pf.submit(staged.pop(0), offsets=offsets.cuda())
+    else:
+        h = pf.submit([w.pin_memory() for w in windows[0]], offsets=offsets.cuda())   # host ids: H2D rides the side stream
     for k in range(len(windows)):
         slots = h.wait()
         oslots = omodel.cache_weight_mgr.prepare_ids(torch.cat(windows[k]))
@@ -523,7 +557,12 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
             out = model(s, offsets.cuda())
             out.backward(g.cuda())
             outs.append(out)
-            if early and j == 0 and k + 1 < len(windows):
+            if early == "staged" and j == 0:
+                if k + 1 < len(windows):
+                    h = pf.submit(staged.pop(k + 1), offsets=offsets.cuda())
+                if k + 2 < len(windows):
+                    staged[k + 2] = pf.stage(pinned[k + 2])
+            elif early and j == 0 and k + 1 < len(windows):
                 h = pf.submit([w.cuda() for w in windows[k + 1]], offsets=offsets.cuda())
         pf.window_enqueued()
         if not early and k + 1 < len(windows):
