@@ -285,6 +285,7 @@ def run_b200(args):
         def __init__(self, batches, host_inputs, overlap=overlap, stage_ids=None):
             self.batches, self.host, self.overlap = batches, host_inputs, overlap
             self.stage_ids = args.stage_ids if stage_ids is None else stage_ids
+            self.submit_before = args.submit_before       # window w+1 goes out before (not after) the first step of w
             self.w, self.slots, self.handles, self.staged, self.h2d = -1, None, {}, {}, 0
             self.trace = []
             self.plan = dict(offsets=offsets) if not args.no_plan_side else {}
@@ -324,6 +325,9 @@ def run_b200(args):
                     if self.overlap:
                         self.submit(w)           # only the very first window of an arm is not in flight already
                         self.slots = torch.chunk(self.handles.pop(w).wait(), P)
+                        if self.submit_before:
+                            self.submit(w + 1)
+                            self.stage(w + 2)
                     else:
                         win = torch.cat([b.to(dev, non_blocking=True) for b in self.ids(w)])
                         self.h2d += P * n_b * 8 if self.host else 0
@@ -337,7 +341,7 @@ def run_b200(args):
                 if self.host:
                     result_host.copy_(out.view(-1)[:D], non_blocking=True)
                     d2h += D * 4
-                if self.overlap and j == 0:
+                if self.overlap and j == 0 and not self.submit_before:
                     self.submit(w + 1)
                     self.stage(w + 2)
                 if self.overlap and j == P - 1:
@@ -405,16 +409,28 @@ def run_b200(args):
             name, _, kv = spec.partition(":")
             env = dict(x.split("=") for x in kv.split(",") if x)
             prio = int(env.pop("PRIORITY", -1))
+            early_done = env.pop("EARLY_DONE", None)
+            submit_before = env.pop("SUBMIT_BEFORE", None)
+            cprio = env.pop("COMPUTE_PRIORITY", None)
             saved = {k: os.environ.get(k) for k in env}
             os.environ.update(env)
             main_pf = prefetcher["pf"]
             prefetcher["pf"] = ce.LookaheadPrefetcher(model, priority=prio, deferred_errors=world > 1)
+            if early_done is not None:
+                prefetcher["pf"].early_done = bool(int(early_done))
             # three untimed windows first: every ring buffer of the new driver has been allocated once
             r = Runner([sample_ids(rows_dev, B, gen, dev) for _ in range((windows + 3) * P)], False)
-            r.run(0, 3 * P + W)
-            ab.setdefault(name, {"settings": kv, "ms_per_step": []})["ms_per_step"].append(
-                round(timed(r, 3 * P + W, K)[0] / K, 4))
-            r.finish()
+            if submit_before is not None:
+                r.submit_before = bool(int(submit_before))
+            torch.cuda.synchronize()
+            # COMPUTE_PRIORITY: forward / backward on a stream of that priority instead of the default stream
+            cstream = torch.cuda.Stream(priority=int(cprio)) if cprio is not None else torch.cuda.current_stream()
+            with torch.cuda.stream(cstream):
+                r.run(0, 3 * P + W)
+                ab.setdefault(name, {"settings": kv, "ms_per_step": []})["ms_per_step"].append(
+                    round(timed(r, 3 * P + W, K)[0] / K, 4))
+                r.finish()
+            torch.cuda.synchronize()
             prefetcher["pf"].close()
             prefetcher["pf"] = main_pf
             # the main driver's settings are back in force (close() restored what it found: two-window protection)
@@ -704,6 +720,8 @@ def main():
     ap.add_argument("--ab", default="", help="'name:ENV=V,ENV2=V2;name2:PRIORITY=0' -- time the device-resident arm again "
                                              "under these settings in the same process")
     ap.add_argument("--ab-reps", type=int, default=3)
+    ap.add_argument("--submit-before", action="store_true",
+                    help="submit window w+1 to the look-ahead driver before the first step of window w, not after it")
     ap.add_argument("--e2e-ab", action="store_true", help="also time the end-to-end arm with the other ids-H2D order")
     ap.add_argument("--trace-steps", action="store_true", help="print GPU / host time between consecutive timed steps")
     ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")

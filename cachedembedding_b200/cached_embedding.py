@@ -55,11 +55,12 @@ class BackwardPlan:
     """The gradient-independent half of a batch's fused backward, made ahead of time: either a private plan inside
     `workspace` (cebag_bag_backward_plan) or the batch's segment of a window plan (cebag_bag_backward_plan_window:
     `keys` / `vals` / `mask` point into the window's sort workspace, `workspace` is this batch's scratch)."""
-    __slots__ = ("workspace", "nbytes", "offsets_ptr", "tag", "keep", "keys", "vals", "mask")
+    __slots__ = ("workspace", "nbytes", "offsets_ptr", "tag", "keep", "keys", "vals", "mask", "ready")
 
-    def __init__(self, workspace, nbytes, offsets_ptr, tag, keep, keys=None, vals=None, mask=0):
+    def __init__(self, workspace, nbytes, offsets_ptr, tag, keep, keys=None, vals=None, mask=0, ready=None):
         self.workspace, self.nbytes, self.offsets_ptr, self.tag, self.keep = workspace, nbytes, offsets_ptr, tag, keep
         self.keys, self.vals, self.mask = keys, vals, mask
+        self.ready = ready      # event recorded on the planning stream after the plan: its consumer waits for it
 
     def apply(self, args) -> int:
         """Point `args` at the plan; returns the workspace_has_plan value for cebag_bag_backward_fused."""
@@ -107,6 +108,8 @@ class _CachedBagFunction(torch.autograd.Function):
                 has_plan = 0
                 if plan is not None:
                     ws = plan.workspace
+                    if plan.ready is not None:       # made on another stream (look-ahead): may still be running
+                        torch.cuda.current_stream().wait_event(plan.ready)
                     ws.record_stream(torch.cuda.current_stream())
                     has_plan = plan.apply(a)
                 else:
@@ -310,11 +313,13 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         ws = workspace_factory(nbytes) if workspace_factory is not None else \
             torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
         _lib.check(lib.cebag_bag_backward_plan(ctypes.byref(a), ws.data_ptr(), nbytes, _stream_ptr()))
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
         if not hasattr(self, "_bwd_plans"):
             self._bwd_plans = {}
         # the plan is only valid for these very tensors: keep them alive so that their addresses cannot be recycled
         self._bwd_plans[(slot_ids.data_ptr(), slot_ids.numel())] = BackwardPlan(ws, nbytes, offsets.data_ptr(), tag,
-                                                                               (slot_ids, offsets))
+                                                                               (slot_ids, offsets), ready=ready)
         return True
 
     def plan_backward_window(self, chunks, offsets_list, layout="bag_major", layout_batch=0, window_factory=None,
@@ -349,6 +354,8 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
         mask = ctypes.c_uint32(0)
         _lib.check(lib.cebag_bag_backward_plan_window(args, P, wws.data_ptr(), wbytes, keys, vals, ctypes.byref(mask),
                                                       _stream_ptr()))
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
         if not hasattr(self, "_bwd_plans"):
             self._bwd_plans = {}
         for j, (chunk, off) in enumerate(zip(chunks, offs)):
@@ -356,7 +363,7 @@ class CachedEmbeddingBag(BaseEmbeddingBag):
             scratch = scratch_factory(j, nbytes) if scratch_factory is not None else \
                 torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
             self._bwd_plans[(chunk.data_ptr(), chunk.numel())] = BackwardPlan(
-                scratch, nbytes, off.data_ptr(), tag, (chunk, off, wws), keys[j], vals[j], int(mask.value))
+                scratch, nbytes, off.data_ptr(), tag, (chunk, off, wws), keys[j], vals[j], int(mask.value), ready=ready)
         return True
 
     def drop_backward_plans(self, tag=None):

@@ -553,7 +553,7 @@ int plan_sorted_backward(const cebag_bag_args* a, const BagParams& p, const BwdL
     const bool fast = (a->mode == CEBAG_MODE_SUM && a->per_sample_weights == nullptr);
     {
         KernelScope scope(kKernBagOf, stream, fast ? 1 : 2);
-        bag_of_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, bag_of);
+        bag_of_kernel<<<grid_for(a->num_bags, 256, env_int("CEBAG_PLAN_CTAS_PER_SM", 8)), 256, 0, stream>>>(p, bag_of);
         CEBAG_LAUNCH_CHECK();
         if (!fast) {
             lookup_weight_kernel<<<grid_for(a->num_bags, 256, 8), 256, 0, stream>>>(p, wts);

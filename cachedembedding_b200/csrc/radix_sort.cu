@@ -186,7 +186,7 @@ struct SortLayout {
 // keys per thread of the pass kernels: 8 (default: twice the tiles, 6 CTAs per SM -- the kernels are latency-bound, the
 // data sits in L2) or 16 (CEBAG_SORT_ITEMS=16)
 int sort_items() {
-    static const int items = env_int("CEBAG_SORT_ITEMS", 8) >= 16 ? 16 : 8;
+    const int items = env_int("CEBAG_SORT_ITEMS", 8) >= 16 ? 16 : 8;      // read per call
     return items;
 }
 
@@ -248,7 +248,8 @@ int radix_sort_impl(const int64_t* slot_ids, int64_t n, int key_bits, void* work
     // and the step faster (0.539 vs 0.570 ms at Criteo-1TB) -- it takes fewer SM slots from kernels that need them.
     const int cta_cap = env_int("CEBAG_SORT_CTAS", kNumSMs);
     const int pass_grid = cta_cap > 0 && cta_cap < tiles ? cta_cap : tiles;
-    const int hgrid = (int)(ceil_div(n, kHistTile) < kNumSMs * 4 ? ceil_div(n, kHistTile) : kNumSMs * 4);
+    const int64_t hcap = (int64_t)kNumSMs * env_int("CEBAG_SORT_HIST_CTAS_PER_SM", 4);
+    const int hgrid = (int)(ceil_div(n, kHistTile) < hcap ? ceil_div(n, kHistTile) : hcap);
     const bool first_is_i64 = slot_ids != nullptr;
     if (first_is_i64) sort_histogram_kernel<int64_t><<<hgrid, kSortThreads, 0, stream>>>(slot_ids, n, passes, key_bits, hist);
     else sort_histogram_kernel<uint32_t><<<hgrid, kSortThreads, 0, stream>>>(kbuf[1], n, passes, key_bits, hist);

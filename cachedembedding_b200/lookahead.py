@@ -108,6 +108,9 @@ class LookaheadPrefetcher:
         self.copy_stream = torch.cuda.Stream(device=self.device, priority=priority) if copy_stream else None
         self.deferred_errors = deferred_errors
         self.window_plan = None            # None: one sort per window if it fits L2, else one per batch; True / False force
+        # True: the handle's completion event is recorded BEFORE the backward plans, so the window's first forward does
+        # not wait for the sorts of all its batches; every plan carries its own event, which its backward waits for
+        self.early_done = True
         self._saved_protect = self.mgr.protect_windows
         self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
@@ -218,6 +221,9 @@ class LookaheadPrefetcher:
                 slot_ids = mgr.prepare_ids(ids_dev, out=ring)
                 rows_done = mgr._rows_ready
                 mgr._rows_ready = None             # the handle carries it; forward() of the bag need not wait again
+                done = torch.cuda.Event()
+                if self.early_done:
+                    done.record(side)
                 if offsets is not None and self.bag is not None:
                     # the gradient-independent half of every batch's fused backward also runs here, off the critical
                     # path (the side stream has passed the fence by now: the plan buffers of window w-2 are free);
@@ -242,8 +248,8 @@ class LookaheadPrefetcher:
                         for j, (chunk, off) in enumerate(zip(chunks, offs)):
                             self.bag.plan_backward(chunk, off, layout, layout_batch, tag=slot,
                                                    workspace_factory=lambda n, p=slot, j=j: self._plan_buffer(p, j, n))
-                done = torch.cuda.Event()
-                done.record(side)
+                if not self.early_done:
+                    done.record(side)
         finally:
             mgr._copy_stream, mgr._victims_ready = None, None
         if staged is not None:

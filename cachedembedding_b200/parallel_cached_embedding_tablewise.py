@@ -191,6 +191,8 @@ class ParallelCachedEmbeddingBagTablewise(CachedEmbeddingBag):
                id(consumer))
         entry = self._step_graphs.get(key)
         self.cache_weight_mgr.wait_rows()
+        if plan.ready is not None:       # the plan was made on the look-ahead side stream and may still be running
+            torch.cuda.current_stream().wait_event(plan.ready)
         if entry is None:
             lib = _lib.load()
             weight = self.cache_weight_mgr.cuda_cached_weight
