@@ -400,6 +400,15 @@ def run_b200(args):
     hist0 = len(mgr.num_miss_history)
     ms_total, _, _ = timed(value_runner, W, K)
     value_runner.finish()
+    gpu_launches = _lib.launch_count() + getattr(model, "graph_launches", 0) - launches0
+    miss_u = sum(mgr.num_miss_history[hist0:])
+    hit_u = sum(mgr.num_hits_history[hist0:])
+    evicted = sum(mgr.num_write_back_history[hist0:])
+    miss_ratio_lookups = mgr._cache_miss / max(mgr._total_cache, 1)
+    if args.trace_steps and rank == 0:
+        tr = [t for t in value_runner.trace if t[0] >= W]
+        for (s0, e0, h0), (s1, e1, h1) in zip(tr[:-1], tr[1:]):
+            print(f"step {s1}: gpu +{e0.elapsed_time(e1):.3f} ms, host +{(h1 - h0) * 1e3:.3f} ms", file=sys.stderr)
     # --ab: the same timed loop again under other settings (environment knobs the library reads per call, PRIORITY =
     # stream priority of the look-ahead driver), fresh ids each, same process and box: A/B records, not the headline
     ab = {}
@@ -444,11 +453,6 @@ def run_b200(args):
     for rec in ab.values():
         xs = sorted(rec["ms_per_step"])
         rec["median"] = xs[len(xs) // 2]
-    gpu_launches = _lib.launch_count() + getattr(model, "graph_launches", 0) - launches0
-    miss_u = sum(mgr.num_miss_history[hist0:])
-    hit_u = sum(mgr.num_hits_history[hist0:])
-    evicted = sum(mgr.num_write_back_history[hist0:])
-    miss_ratio_lookups = mgr._cache_miss / max(mgr._total_cache, 1)
 
     # ---- per-kernel timers on a replay of the same steps (CUDA events on the launching stream) ------------------
     # (look-ahead off for this replay: every kernel is alone on the GPU, so its event-bracketed time is its own)

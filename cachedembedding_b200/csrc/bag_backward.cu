@@ -187,8 +187,9 @@ bag_backward_phase1_kernel(const BagParams p, const UpdateParams up, const uint3
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane_id() & ~(LANES - 1)));
     const int gshift = lane_id() & ~(LANES - 1);
-    const int64_t group = ((int64_t)blockIdx.x * kBwdThreads + threadIdx.x) / LANES;
-    const int64_t num_groups = (int64_t)gridDim.x * kBwdThreads / LANES;
+    // groups are independent: the CTA size is a launch parameter (blockDim.x = 128 or 256)
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * blockDim.x / LANES;
     const int chunks = p.chunks;
     const VT* __restrict__ cachev = reinterpret_cast<const VT*>(up.cache);
     const uint32_t pad = p.padding_idx >= 0 ? (uint32_t)p.padding_idx : 0xffffffffu;
@@ -613,14 +614,17 @@ int run_sorted_backward(const cebag_bag_args* a, const float* grad_out, float* t
     // sorted positions in flight per group (tunable: CEBAG_BWD_UNROLL = 4 | 8; 8 only for one chunk per lane)
     const int unroll_env = env_int("CEBAG_BWD_UNROLL", 4);
     const int bwd_ctas_per_sm = env_int("CEBAG_BWD_CTAS_PER_SM", 32);
+    // CTA size of phase 1 (128 | 256).  Smaller CTAs = finer granularity when a side-stream kernel takes registers on
+    // the SM: with 74 registers only three 256-thread CTAs are resident, and a guest CTA evicts a third of them.
+    const int bwd_threads = env_int("CEBAG_BWD_THREADS", 256) == 128 ? 128 : 256;
 #define LAUNCH_P1(VT, LANES, CPL, FAST, UNROLL)                                                                     \
-    bag_backward_phase1_kernel<VT, LANES, CPL, OPT, FAST, UNROLL><<<grid, kBwdThreads, 0, stream>>>(                \
+    bag_backward_phase1_kernel<VT, LANES, CPL, OPT, FAST, UNROLL><<<grid, bwd_threads, 0, stream>>>(                \
         p, up, keys, vals, bag_of, wts, grad_out, scratch, flags, L.num_chunks)
 #define LAUNCH_BWD(VT, LANES, CPL)                                                                                  \
     do {                                                                                                            \
         {                                                                                                           \
             KernelScope scope1(kKernBwdPhase1, stream);                                                             \
-            int grid = grid_for(L.num_chunks * LANES, kBwdThreads, bwd_ctas_per_sm);                                \
+            int grid = grid_for(L.num_chunks * LANES, bwd_threads, bwd_ctas_per_sm * (kBwdThreads / bwd_threads));  \
             if (fast) {                                                                                             \
                 if (unroll_env >= 8 && CPL == 1) LAUNCH_P1(VT, LANES, CPL, true, 8);                                \
                 else LAUNCH_P1(VT, LANES, CPL, true, 4);                                                            \

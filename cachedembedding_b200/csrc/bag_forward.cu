@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(kFwdThreads)
 bag_forward_kernel(const BagParams p, float* __restrict__ out) {
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned gmask = group_mask<LANES>();
-    const int64_t group = ((int64_t)blockIdx.x * kFwdThreads + threadIdx.x) / LANES;
-    const int64_t num_groups = (int64_t)gridDim.x * kFwdThreads / LANES;
+    // groups are independent: the CTA size is a launch parameter (blockDim.x = 128 or 256)
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t num_groups = (int64_t)gridDim.x * blockDim.x / LANES;
     const VT* __restrict__ cache = reinterpret_cast<const VT*>(p.cache);
     const int chunks = p.chunks;
     const bool mean = !FAST && p.mode == CEBAG_MODE_MEAN;
@@ -201,19 +202,20 @@ extern "C" int cebag_bag_forward(const cebag_bag_args* a, float* out, void* stre
     const int unroll_env = env_int("CEBAG_FWD_UNROLL", 4);
     const int ctas_per_sm = env_int("CEBAG_FWD_CTAS_PER_SM", 32);
     const int ld_policy = env_int("CEBAG_FWD_LD", 1);
+    const int fwd_threads = env_int("CEBAG_FWD_THREADS", 256) == 128 ? 128 : 256;     // CTA size
     const bool fast_path = a->per_sample_weights == nullptr && a->mode == CEBAG_MODE_SUM && a->padding_idx < 0 &&
                            a->layout == CEBAG_LAYOUT_BAG_MAJOR;
 #define LAUNCH_FWD_U(VT, LANES, CPL, UNROLL)                                                             \
     do {                                                                                                 \
         int64_t groups = ceil_div(p.num_bags, LANES);                                                    \
-        int grid = grid_for(groups * LANES, kFwdThreads, ctas_per_sm);                                   \
+        int grid = grid_for(groups * LANES, fwd_threads, ctas_per_sm * (kFwdThreads / fwd_threads));     \
         if (fast_path && ld_policy == 0)                                                                 \
-            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 0><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 0><<<grid, fwd_threads, 0, stream>>>(p, out);          \
         else if (fast_path && ld_policy == 2)                                                            \
-            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 2><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 2><<<grid, fwd_threads, 0, stream>>>(p, out);          \
         else if (fast_path)                                                                              \
-            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 1><<<grid, kFwdThreads, 0, stream>>>(p, out);          \
-        else bag_forward_kernel<VT, LANES, CPL, UNROLL, false, 1><<<grid, kFwdThreads, 0, stream>>>(p, out);        \
+            bag_forward_kernel<VT, LANES, CPL, UNROLL, true, 1><<<grid, fwd_threads, 0, stream>>>(p, out);          \
+        else bag_forward_kernel<VT, LANES, CPL, UNROLL, false, 1><<<grid, fwd_threads, 0, stream>>>(p, out);        \
     } while (0)
 #define LAUNCH_FWD(VT, LANES, CPL)                                                                       \
     do {                                                                                                 \
