@@ -395,6 +395,8 @@ def run_b200(args):
     # K timed steps alone are shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local) if rank == 0 else None
     value_runner = Runner(arms["value"], False)
+    if args.trace_steps and prefetcher["pf"] is not None:
+        prefetcher["pf"].trace = []
     value_runner.run(0, W)
     launches0 = _lib.launch_count() + getattr(model, "graph_launches", 0)
     hist0 = len(mgr.num_miss_history)
@@ -409,6 +411,20 @@ def run_b200(args):
         tr = [t for t in value_runner.trace if t[0] >= W]
         for (s0, e0, h0), (s1, e1, h1) in zip(tr[:-1], tr[1:]):
             print(f"step {s1}: gpu +{e0.elapsed_time(e1):.3f} ms, host +{(h1 - h0) * 1e3:.3f} ms", file=sys.stderr)
+        if prefetcher["pf"] is not None and prefetcher["pf"].trace:
+            # where the side / copy stream work of every submitted window sits between the steps (ms since the end of
+            # the first timed step; step s ends at "step s" below)
+            torch.cuda.synchronize()
+            t0 = tr[0][1]
+            print("step ends: " + " ".join(f"{s}:{t0.elapsed_time(e):.2f}" for s, e, _ in tr), file=sys.stderr)
+            for rec in prefetcher["pf"].trace:
+                try:
+                    print("window %d: " % rec["window"] + " ".join(
+                        f"{k}={t0.elapsed_time(rec[k]):.2f}" for k in ("side_start", "prepared", "planned", "filled", "copied")
+                        if k in rec), file=sys.stderr)
+                except Exception as exc:        # an event of a window outside the timed region
+                    print("window %d: %s" % (rec["window"], exc), file=sys.stderr)
+            prefetcher["pf"].trace = None
     # --ab: the same timed loop again under other settings (environment knobs the library reads per call, PRIORITY =
     # stream priority of the look-ahead driver), fresh ids each, same process and box: A/B records, not the headline
     ab = {}
@@ -421,6 +437,10 @@ def run_b200(args):
             early_done = env.pop("EARLY_DONE", None)
             submit_before = env.pop("SUBMIT_BEFORE", None)
             cprio = env.pop("COMPUTE_PRIORITY", None)
+            dma = env.pop("DMA", None)                  # parked victims leave through the copy engine + host threads
+            saved_dma = mgr.dma_writeback
+            if dma is not None:
+                mgr.dma_writeback = bool(int(dma))
             saved = {k: os.environ.get(k) for k in env}
             os.environ.update(env)
             main_pf = prefetcher["pf"]
@@ -442,6 +462,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             prefetcher["pf"].close()
             prefetcher["pf"] = main_pf
+            mgr.dma_writeback = saved_dma
             # the main driver's settings are back in force (close() restored what it found: two-window protection)
             mgr.protect_windows = max(2, mgr.protect_windows)
             mgr._defer_results = True

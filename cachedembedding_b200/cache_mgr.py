@@ -254,7 +254,8 @@ class CachedParamMgr(nn.Module):
         cstream = self._active_copy_stream()
         events = None
         if cstream is not None:
-            rows_done, wb_done = torch.cuda.Event(), torch.cuda.Event()
+            # timing-enabled: a look-ahead driver that traces its pipeline reads the end of the fill from rows_done
+            rows_done, wb_done = torch.cuda.Event(enable_timing=True), torch.cuda.Event()
             rows_done.record(cstream)          # instantiates the events; re-recorded by the library after the copies
             wb_done.record(cstream)
             ws.copy_stream = cstream.cuda_stream

@@ -111,6 +111,7 @@ class LookaheadPrefetcher:
         # True: the handle's completion event is recorded BEFORE the backward plans, so the window's first forward does
         # not wait for the sorts of all its batches; every plan carries its own event, which its backward waits for
         self.early_done = True
+        self.trace = None                  # a list: submit() appends timing events of its side / copy stream work
         self._saved_protect = self.mgr.protect_windows
         self._saved_defer = self.mgr._defer_results
         self.mgr.protect_windows = max(2, self.mgr.protect_windows)
@@ -201,8 +202,18 @@ class LookaheadPrefetcher:
         mgr._copy_stream, mgr._victims_ready = self.copy_stream, fence
         if self.copy_stream is None:
             side.wait_event(fence)
+        tr = None
+        if self.trace is not None:
+            tr = {"window": w}
+            self.trace.append(tr)
+
+        def mark(name, stream):
+            if tr is not None:
+                tr[name] = torch.cuda.Event(enable_timing=True)
+                tr[name].record(stream)
         try:
             with torch.cuda.stream(side):
+                mark("side_start", side)
                 if staged is not None:
                     parts = list(torch.split(staged.tensor, staged.sizes))
                     ids_dev = staged.tensor
@@ -224,6 +235,11 @@ class LookaheadPrefetcher:
                 done = torch.cuda.Event()
                 if self.early_done:
                     done.record(side)
+                mark("prepared", side)
+                if tr is not None and rows_done is not None:
+                    tr["filled"] = rows_done
+                if self.copy_stream is not None:
+                    mark("copied", self.copy_stream)      # fill + write-back of this window's rows
                 if offsets is not None and self.bag is not None:
                     # the gradient-independent half of every batch's fused backward also runs here, off the critical
                     # path (the side stream has passed the fence by now: the plan buffers of window w-2 are free);
@@ -250,6 +266,7 @@ class LookaheadPrefetcher:
                                                    workspace_factory=lambda n, p=slot, j=j: self._plan_buffer(p, j, n))
                 if not self.early_done:
                     done.record(side)
+                mark("planned", side)
         finally:
             mgr._copy_stream, mgr._victims_ready = None, None
         if staged is not None:
