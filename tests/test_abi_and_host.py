@@ -308,6 +308,15 @@ def test_reference_import_lines_resolve_after_install():
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
 
 
+@pytest.mark.parametrize("D", [516, 130, 1024])
+def test_unsupported_row_width_is_rejected_at_construction(D):
+    """Rows live in the registers of one warp: up to 512 floats (multiple of 4) / 128 floats otherwise.  Wider tables
+    fail when the module is built -- before any device memory is touched -- not at the first forward."""
+    import cachedembedding_b200 as ce
+    with pytest.raises(NotImplementedError, match="floats are not supported"):
+        ce.CachedEmbeddingBag(10, D, _weight=torch.zeros(10, D))
+
+
 def test_limit_buff_index_copyer_chunks():
     from cachedembedding_b200 import LimitBuffIndexCopyer
     gen = torch.Generator().manual_seed(0)
