@@ -162,6 +162,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.stage_ids == "auto":
+        args.stage_ids = "after-fill" if world == 1 else "off"
     wl = dict(WORKLOADS[args.workload])
     if args.cache_ratio > 0:
         wl["cache_ratio"] = args.cache_ratio
@@ -284,7 +286,7 @@ def run_b200(args):
 
         def __init__(self, batches, host_inputs, overlap=overlap, stage_ids=None):
             self.batches, self.host, self.overlap = batches, host_inputs, overlap
-            self.stage_ids = args.stage_ids if stage_ids is None else stage_ids
+            self.stage_ids = args.stage_ids if stage_ids is None else stage_ids        # "off" | "early" | "after-fill"
             self.submit_before = args.submit_before       # window w+1 goes out before (not after) the first step of w
             self.w, self.slots, self.handles, self.staged, self.h2d = -1, None, {}, {}, 0
             self.trace = []
@@ -295,9 +297,9 @@ def run_b200(args):
 
         def stage(self, w):
             """Host ids only: their H2D copies start one window before the window's prepare_ids (own stream)."""
-            if (self.host and self.stage_ids and w not in self.staged and w not in self.handles
+            if (self.host and self.stage_ids != "off" and w not in self.staged and w not in self.handles
                     and (w + 1) * P <= len(self.batches)):
-                self.staged[w] = prefetcher["pf"].stage(self.ids(w))
+                self.staged[w] = prefetcher["pf"].stage(self.ids(w), after_last_fill=self.stage_ids == "after-fill")
                 self.h2d += P * n_b * 8
 
         def submit(self, w):
@@ -488,11 +490,11 @@ def run_b200(args):
     result_host = torch.empty(D, dtype=torch.float32).pin_memory()
     e2e_ab = None
     if args.e2e_ab and overlap:      # both ids-H2D orders on the same box, interleaved, fresh ids (A/B record, not the headline)
-        e2e_ab = {"staged": [], "unstaged": []}
+        e2e_ab = {m: [] for m in args.e2e_ab_modes.split(",")}
         for rep in range(args.ab_reps):
-            for mode in ("unstaged", "staged"):
+            for mode in e2e_ab:
                 hb = [sample_ids(rows_dev, B, gen, dev).cpu().pin_memory() for _ in range(windows * P)]
-                r = Runner(hb, True, stage_ids=mode == "staged")
+                r = Runner(hb, True, stage_ids=mode)
                 r.run(0, W)
                 e2e_ab[mode].append(round(timed(r, W, K)[0] / K, 4))
                 r.finish()
@@ -608,9 +610,9 @@ def run_b200(args):
         "kernels": kernels,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                 "ms_per_step": e2e_ms / K,
-                "ids_h2d": ("side stream, right before the window's prepare_ids" if not args.stage_ids or not overlap else
-                            "own stream, one window ahead of the window's prepare_ids (LookaheadPrefetcher.stage); every "
-                            "timed window still copies one window of ids"),
+                "ids_h2d": ("side stream, right before the window's prepare_ids" if args.stage_ids == "off" or not overlap else
+                            "own stream, one window ahead of the window's prepare_ids (LookaheadPrefetcher.stage, "
+                            + args.stage_ids + "); every timed window still copies one window of ids"),
                 "note": ("ids of every batch come from pinned host memory inside the timed region; the pooled embeddings "
                          "stay in HBM by design (their consumer is the dense part of the model), one pooled row per step "
                          "is read back as the result; the D2H traffic that matters -- evicted rows going back to the "
@@ -732,11 +734,13 @@ def main():
                     help="auto: the reference's table->rank map where it has one, else the snake; snake: always")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: NCCL all-to-all instead of peer-memory kernels")
     ap.add_argument("--no-plan-side", action="store_true", help="keep the backward's radix sort on the compute stream")
-    ap.add_argument("--stage-ids", action="store_true",
+    ap.add_argument("--stage-ids", default="auto", choices=["auto", "off", "early", "after-fill"],
                     help="end-to-end arm: copy a window's ids H2D one window earlier on their own stream "
-                         "(LookaheadPrefetcher.stage) instead of on the side stream right before its prepare_ids; "
-                         "measured SLOWER at Criteo-1TB (0.78-0.82 vs 0.58-0.65 ms per step): the early copy shares the "
-                         "PCIe read direction with the previous window's fill, which the forward waits for")
+                         "(LookaheadPrefetcher.stage) instead of on the side stream right before its prepare_ids. "
+                         "'early' = as soon as the host has them: measured SLOWER at Criteo-1TB (0.78-0.82 vs 0.58-0.65 ms "
+                         "per step) -- the copy shares the PCIe read direction with the previous window's fill, which "
+                         "the forward waits for; 'after-fill' = the copy waits for that fill on the device: 0.56 vs "
+                         "0.65 ms per step, the default on one GPU ('auto'; N > 1 keeps 'off': not measured there)")
     ap.add_argument("--parallelism", default="table", choices=["table", "column"],
                     help="N > 1: table-wise sharding (BASELINE.json configs[3]) or the reference's default column-wise bag")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the untimed parity leg")
@@ -747,6 +751,7 @@ def main():
     ap.add_argument("--ab-reps", type=int, default=3)
     ap.add_argument("--submit-before", action="store_true",
                     help="submit window w+1 to the look-ahead driver before the first step of window w, not after it")
+    ap.add_argument("--e2e-ab-modes", default="off,after-fill,early")
     ap.add_argument("--e2e-ab", action="store_true", help="also time the end-to-end arm with the other ids-H2D order")
     ap.add_argument("--trace-steps", action="store_true", help="print GPU / host time between consecutive timed steps")
     ap.add_argument("--verify-only", action="store_true", help="N > 1: run the parity leg and stop")

@@ -121,6 +121,7 @@ class LookaheadPrefetcher:
         self._ids_stream = None                           # H2D copies of stage()
         self._ids_ring = [None] * _RING                   # the last StagedIds of every ring buffer
         self._staged = 0
+        self._last_rows_done = None                       # fill event of the most recent submit (stage(after_last_fill))
         self._fences = {}                  # window index -> event recorded after its compute was enqueued
         self._submitted = 0                # windows submitted since the last drain
         self._enqueued = 0                 # windows whose compute has been enqueued since the last drain
@@ -144,12 +145,14 @@ class LookaheadPrefetcher:
             ev.record(torch.cuda.current_stream(self.device))
         return ev
 
-    def stage(self, ids) -> StagedIds:
+    def stage(self, ids, after_last_fill: bool = False) -> StagedIds:
         """Start the H2D copies of a window's ids (a tensor or the list of the window's batches, normally in pinned host
         memory) on the driver's ids stream and return at once.  Nothing of the cache is touched: call it as early as
         the host has the batches -- one window before `submit(staged)` is what it takes to get the copy out of the
         window's critical chain.  The device buffer is one of three ring buffers; it is recycled once the submit that
-        consumed its previous content has finished on the side stream."""
+        consumed its previous content has finished on the side stream.
+        `after_last_fill`: the copies wait (on the device) for the fill of the most recently submitted window -- the
+        missed rows and the ids share the PCIe read direction, and the fill is what the next forward waits for."""
         parts = ids if isinstance(ids, (list, tuple)) else [ids]
         sizes = [t.numel() for t in parts]
         total = sum(sizes)
@@ -160,6 +163,8 @@ class LookaheadPrefetcher:
         self._staged += 1
         prev = self._ids_ring[k]
         with torch.cuda.stream(h2d):
+            if after_last_fill and self._last_rows_done is not None:
+                h2d.wait_event(self._last_rows_done)
             if prev is not None and prev.done is not None and prev.tensor.numel() == total:
                 h2d.wait_event(prev.done)            # the readers of the old content: that window's prepare_ids
                 buf = prev.tensor
@@ -232,6 +237,7 @@ class LookaheadPrefetcher:
                 slot_ids = mgr.prepare_ids(ids_dev, out=ring)
                 rows_done = mgr._rows_ready
                 mgr._rows_ready = None             # the handle carries it; forward() of the bag need not wait again
+                self._last_rows_done = rows_done
                 done = torch.cuda.Event()
                 if self.early_done:
                     done.record(side)
