@@ -526,7 +526,8 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
     slots before the fill.  dma: parked victims leave through the copy engine + host threads ("slow": every host
     scatter is delayed by 20 ms, so rows that are missed again are served from the staging buffer or not at all).
     early = "staged": the ids of window k+2 leave pinned host memory on the driver's ids stream (pf.stage) while window
-    k trains, and window k+1 is submitted from its staged ids (three ring buffers, each reused twice here)."""
+    k trains -- behind the fill of window k+1, the order bench.py's end-to-end arm uses -- and window k+1 is submitted
+    from its staged ids (three ring buffers, each reused twice here)."""
     ce = _mods()
     if dma == "slow":
         monkeypatch.setenv("CEBAG_WB_DELAY_US", "20000")
@@ -567,8 +568,8 @@ def test_lookahead_prefetcher_matches_oracle_with_two_window_protection(strategy
             if early == "staged" and j == 0:
                 if k + 1 < len(windows):
                     h = pf.submit(staged.pop(k + 1), offsets=offsets.cuda())
-                if k + 2 < len(windows):
-                    staged[k + 2] = pf.stage(pinned[k + 2])
+                if k + 2 < len(windows):      # held back on the device until the fill of window k+1 has finished
+                    staged[k + 2] = pf.stage(pinned[k + 2], after_last_fill=True)
             elif early and j == 0 and k + 1 < len(windows):
                 h = pf.submit([w.cuda() for w in windows[k + 1]], offsets=offsets.cuda())
         pf.window_enqueued()
