@@ -15,9 +15,11 @@ timers end in torch.cuda.synchronize()).  Here three stre
                    with the fill, and host threads scatter them into the table (cache_mgr.dma_writeback); a row that
                    is missed again while its write-back is in flight is filled from the staging buffer
   ids stream     : `stage()` -- the H2D copy of a window's ids from (pinned) host memory, one window further ahead than
-                   its prepare_ids: at Criteo-1TB a window is 109 MB of int64 ids = 2 ms of PCIe, and the chain
-                   ids H2D -> map work -> fill of one window no longer fits under the previous window's compute when
-                   all three run back to back on the side stream
+                   its prepare_ids and (after_last_fill=True) behind the fill of the window submitted last: at
+                   Criteo-1TB a window is 109 MB of int64 ids = 2 ms of PCIe, and the chain ids H2D -> map work -> fill
+                   of one window does not fit under the previous window's compute when all three run back to back
+                   (end to end 0.65 -> 0.56 ms per step); without the hold-back the early copy competes with the fill
+                   for the PCIe read direction and is slower than no staging
 
 prepare_ids never waits for the GPU (cebag_prepare_ids_async), so `submit` costs the host a few dozen kernel launches
 and may be called anywhere inside window k -- the earlier the better: right after the window's first step has been
