@@ -21,6 +21,10 @@ window k+1 is submitted right after the FIRST step of window k; --no-overlap for
 N > 1 first runs an untimed parity leg (bench_verify.py: fused NVLink exchange vs NCCL exchange bit for bit, slot maps,
 pooled sums and tables against the CPU oracle, table-wise and column-wise) and fails the run on a mismatch; the record
 is the line's `parity_check`.  `--parallelism column` times the column-wise bag instead of the table-wise one.
+End-to-end arm (`e2e`): the ids of every batch start in pinned host memory; on one GPU the ids of window k+2 are staged
+H2D on their own stream behind the fill of window k+1 (`--stage-ids`, LookaheadPrefetcher.stage), one pooled row per
+step is read back.  `--ab` / `--e2e-ab` / `--trace-steps` add interleaved in-process A/B samples of launch-shape
+settings, of the ids-H2D orders, and a timeline of the pipeline to the line / stderr.
 `--impl reference` times the CPU oracle port on the host cores.
 """
 from __future__ import annotations
